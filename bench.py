@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Benchmark of the ReReVST per-frame stylization hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): stylized frames/s at 1080p, i.e. 1080x1920 frames reflect-padded to
+1216x2048 exactly as generate_real_video.py:61-83 does, one style, global mode.  A step is one
+frame through TransformerNet.forward.  Rank 0 prints ONE JSON line.
+
+  value      frames/s with the uint8 frames already resident in HBM (device-timed, CUDA events)
+  e2e        frames/s through Stylization.transfer with HOST buffers: pinned uint8 H2D, the
+             whole network, postprocess + crop, fp32 BGR D2H -- every step
+  roofline   tensor-core roofline of the implicit-GEMM convolutions: algorithmic FLOPs per
+             frame / measured time vs MEASURED_PEAKS.json (sustained)
+  cpu_baseline  the CPU oracle (a torch-CPU restatement of the reference, pinned to it by
+             tests/golden) timed on this box's host cores on one full frame
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+SIZES = {"1080p": (1080, 1920), "720p": (720, 1280), "256": (256, 256)}
+METRIC = "stylized frames/sec at 1080p (1/2/4/8 B200) + % conv roofline"
+
+
+def padded_size(h, w):
+    """ReshapeTool, generate_real_video.py:66-78."""
+    nh, nw = h + 128, w + 128
+    nh += (64 - nh % 64) % 64
+    nw += (64 - nw % 64) % 64
+    return nh, nw
+
+
+def reflect_pad(img, nh, nw):
+    """cv2.copyMakeBorder(..., BORDER_REFLECT) of generate_real_video.py:80-82 (edge pixel repeated)."""
+    h, w, _ = img.shape
+    return np.pad(img, ((64, nh - 64 - h), (64, nw - 64 - w), (0, 0)), mode="symmetric")
+
+
+def synthetic_frame(h, w, seed):
+    """Image-like uint8 BGR frame: smooth low-frequency content + mild noise."""
+    rng = np.random.RandomState(seed)
+    coarse = rng.rand(h // 16 + 2, w // 16 + 2, 3).astype(np.float32)
+    img = np.kron(coarse, np.ones((16, 16, 1), np.float32))[:h, :w]
+    k = np.ones(9, np.float32) / 9
+    img = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), 0, img)
+    img = np.apply_along_axis(lambda v: np.convolve(v, k, mode="same"), 1, img)
+    img = img * 255 + rng.randn(h, w, 3) * 4
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def flops_per_frame(h, w):
+    """Algorithmic FLOPs of the 31 convolutions on the per-frame path."""
+    total, hh, ww = 0.0, h, w
+    for idx, cin, cout in ((0, 3, 64), (2, 64, 64), (5, 64, 128), (7, 128, 128), (10, 128, 256),
+                           (12, 256, 256), (14, 256, 256), (16, 256, 256), (19, 256, 512)):
+        total += 2.0 * cin * cout * 9 * hh * ww
+        if idx in (2, 7, 16):
+            hh, ww = hh // 2, ww // 2
+    total += 3 * (2.0 * 512 * 32 * 9 + 2 * 2.0 * 32 * 32 + 2.0 * 32 * 512 * 9) * hh * ww
+    for cin, cout in ((512, 256), (256, 128), (128, 64)):
+        hh, ww = hh * 2, ww * 2
+        total += (2.0 * cin * cout * 9 + 2.0 * cout * cout * 9 + 2.0 * cin * cout) * hh * ww
+    return total + 2.0 * 64 * 3 * 9 * hh * ww
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d["bf16_tflops_sustained"]), hbm=float(d["hbm_gbs"]), src="MEASURED_PEAKS.json (sustained bf16)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for r in self.rows if len(r) >= 7]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons,
+                "power_w_max": max(float(r[2]) for r in rows), "samples": len(rows)}
+
+
+# ------------------------------------------------------------------------------------ reference arm
+
+def cpu_oracle_state(sd, style_u8, seed=7):
+    """Oracle with a small CPU pre-pass (the statistics do not change the per-frame cost)."""
+    from oracle import stylenet
+    o = stylenet.GlobalOracle(sd)
+    o.generate_style_features(stylenet.transform_image(stylenet.numpy2tensor(style_u8[:128, :128])))
+    o.clean()
+    o.add(stylenet.transform_image(stylenet.numpy2tensor(synthetic_frame(128, 128, seed))))
+    o.compute()
+    return o
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU PyTorch path (oracle port; /root/reference does not
+    exist on the GPU box) on all host threads.  A step is a 1/8-frame strip of the padded frame."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import stylenet
+    from rerevst_code_b200.weights import synthetic_state_dict
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    h, w = SIZES[args.size]
+    ph, pw = padded_size(h, w)
+    sh = max(64, (ph // 8) // 8 * 8)
+    frac = (sh * pw) / float(ph * pw)
+    sd = synthetic_state_dict(0)
+    o = cpu_oracle_state(sd, synthetic_frame(512, 512, 1))
+    frame = reflect_pad(synthetic_frame(h, w, 100), ph, pw)[:sh]
+    x = stylenet.transform_image(stylenet.numpy2tensor(frame))
+    steps, warm = args.steps, args.warmup
+    for _ in range(warm):
+        o.forward(x)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.forward(x)
+    dt = (time.perf_counter() - t0) / steps
+    fps = frac / dt
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.size} frames padded to {ph}x{pw}, 1 style, global mode, B=1 (reference loop is serial)",
+                       "frame": [h, w], "padded": [ph, pw]},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"TransformerNet.forward on a {sh}x{pw} strip (1/{round(1 / frac)} of a padded frame) per step, "
+                                       f"scaled by pixel count; torch {torch.__version__} CPU"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ our arm
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", default="1080p", choices=list(SIZES))
+    ap.add_argument("--precision", default=os.environ.get("RRV_PRECISION", "x3"), choices=["x3", "bf16"])
+    ap.add_argument("--kernels", default=os.environ.get("RRV_KERNELS", "auto"), choices=["auto", "ffma", "tc"])
+    ap.add_argument("--samples", type=int, default=4, help="sampled frames of the pre-pass (not timed)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from rerevst_code_b200 import _lib
+    from rerevst_code_b200.framework import Stylization
+    from rerevst_code_b200.weights import synthetic_state_dict
+
+    h, w = SIZES[args.size]
+    ph, pw = padded_size(h, w)
+    sd = synthetic_state_dict(0)
+    fw = Stylization(sd, cuda=True, precision=args.precision, impl=args.kernels)
+    eng = fw.model._eng()
+    style = synthetic_frame(512, 512, 1)
+    fw.prepare_style(style)
+
+    # ---- per-clip pre-pass (not part of the timed per-frame loop; reported separately) ----
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fw.clean()
+    if world > 1:
+        from rerevst_code_b200.dist import sharded_prepass
+        sharded_prepass(fw, [synthetic_frame(h, w, 50 + i) for i in range(max(args.samples, world))], rank, world)
+    else:
+        for i in range(args.samples):
+            fw.add(synthetic_frame(h, w, 50 + i))
+        fw.compute()
+    torch.cuda.synchronize()
+    prepass_s = time.perf_counter() - t0
+
+    nfr = 4
+    host_frames = [reflect_pad(synthetic_frame(h, w, 100 + rank * 16 + i), ph, pw) for i in range(nfr)]
+    dev_frames = [torch.from_numpy(f).unsqueeze(0).to(dev) for f in host_frames]
+    out = torch.empty((1, 3, ph, pw), dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warm):
+        for i in range(warm):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.lib().rrv_launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.lib().rrv_launch_count() - n0
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    # ---- device-resident arm ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms_dev, launches = timed(lambda i: eng.forward(dev_frames[i % nfr], kind=1, out=out), args.steps, args.warmup)
+    clk = clocks.stop() if rank == 0 else None
+    # ---- end-to-end arm: host uint8 in, host fp32 BGR out, every step ----
+    crop = (64, 64, h, w)
+    ms_e2e, _ = timed(lambda i: fw.transfer(host_frames[i % nfr], crop=crop), args.steps, args.warmup)
+
+    # ---- per-launch breakdown of the convolution kernel (CUDA events around each launch) ----
+    eng.profile = []
+    eng.forward(dev_frames[0], kind=1, out=out)
+    torch.cuda.synchronize()
+    layers = [(lbl, a.elapsed_time(b), fl) for lbl, a, b, fl in eng.profile]
+    eng.profile = None
+    conv_ms = sum(t for _, t, _ in layers)
+    conv_flops = sum(f for _, _, f in layers)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    fl = flops_per_frame(ph, pw)
+    fps = world * args.steps / (ms_dev * 1e-3)
+    fps_e2e = world * args.steps / (ms_e2e * 1e-3)
+    achieved = fl * (args.steps / (ms_dev * 1e-3)) / 1e12            # per GPU
+    line = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16x3 (fp32-accurate split operands, fp32 accumulate)" if args.precision == "x3" else "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"{args.size} frames reflect-padded to {ph}x{pw} (generate_real_video.py:61-83), 1 style 512x512, "
+                               f"global mode, random-init weights, B=1 per step, {args.samples} pre-pass samples",
+                   "frame": [h, w], "padded": [ph, pw], "precision": args.precision,
+                   "kernels": {0: "ffma", 1: "tcgen05"}[eng.impl],
+                   "l2": "per-step working set ~10 GB of activations >> 126 MB L2; 4 distinct input frames rotate"},
+        "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": ph * pw * 3, "d2h_bytes_per_step": h * w * 3 * 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["src"],
+                     "flops_per_frame": fl,
+                     "conv_kernel": {"launches_per_frame": len(layers), "ms_per_frame": conv_ms,
+                                     "executed_tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None}},
+        "prepass_s": prepass_s,
+        "layers": [{"layer": lbl, "ms": round(t, 4), "tflops": round(f / (t * 1e-3) / 1e12, 2) if t > 0 else None}
+                   for lbl, t, f in layers],
+    }
+
+    # ---- CPU baseline + full-size parity on the same frame (rank 0, N=1 only) ----
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import stylenet
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        o = stylenet.GlobalOracle(sd)
+        o.F_style = None
+        st = eng.export_clip_state()
+        clip = stylenet.ClipState()
+        for k, v in st["stats"].items():
+            t = v.cpu()
+            clip.stats[k] = stylenet.SavedStat(*[t[i].view(1, -1, 1, 1) for i in range(4)])
+        for k, (a, b) in st["filters"].items():
+            clip.filters[k] = (a.cpu().view(1, 32, 32), b.cpu().view(1, 32, 32))
+        o.clip = clip
+        tabs = eng.style["tabs"]
+        ms_ = {k: stylenet.MeanStd(v[1].cpu().view(1, -1, 1, 1), v[0].cpu().view(1, -1, 1, 1)) for k, v in tabs.items()}
+        o.F_style = stylenet.StyleFeatures(None, ms_["relu1_1"], ms_["relu2_1"], ms_["relu3_1"], ms_["relu4_1"])
+        x = stylenet.transform_image(stylenet.numpy2tensor(host_frames[0]))
+        t0 = time.perf_counter()
+        ref = o.forward(x)
+        dt = time.perf_counter() - t0
+        got = eng.forward(dev_frames[0], kind=1).cpu()
+        err = float((got - ref).abs().max() / ref.abs().max())
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": f"one {ph}x{pw} frame through the oracle's TransformerNet.forward "
+                                          f"(torch {torch.__version__} CPU, {cores} threads), statistics imported from the GPU pre-pass"}
+        line["parity"] = {"rel_linf_vs_cpu_oracle_full_frame": err, "tolerance": 1e-3 if args.precision == "x3" else None}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

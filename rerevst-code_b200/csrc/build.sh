@@ -1,0 +1,17 @@
+#!/bin/bash
+# Builds librerevst_b200.so for sm_100a in-tree (no torch dependency: plain CUDA runtime).
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
+mkdir -p build
+pids=()
+for f in capi conv_ffma conv_tc first_layer pointwise stats warp; do
+  if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ rrv_common.cuh -nt build/$f.o ] || [ ../../include/rerevst_b200.h -nt build/$f.o ] || { [ $f = conv_tc ] && [ -f tc_ptx.cuh ] && [ tc_ptx.cuh -nt build/$f.o ]; }; then
+    $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f.cu -o build/$f.o &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]}"; do wait $p; done
+$NVCC -shared -o librerevst_b200.so build/*.o -lcudart
+echo "built $(pwd)/librerevst_b200.so"

@@ -1,0 +1,192 @@
+// Per-channel statistics of the pre-pass ("Sequence-Level Global Feature Sharing").
+//
+// InstanceNorm.compute (style_network_global.py:59-77) takes mean / biased variance / min / max
+// of the normalised tensor over batch and space in two passes; EncoderStyle.cal_mean_std
+// (:304-315) takes mean and unbiased std; FilterPredictor.compute (:161-172) takes a spatial
+// and batch mean followed by a 64 -> 1024 linear layer.  Here one two-pass reduction produces
+// mergeable partials {count, sum, M2, min, max} in double precision (warp shuffles inside a
+// warp, shared memory across warps, one atomic per channel per block), so that ranks of the
+// frame-parallel driver can all-gather and merge them (Chan et al.) in a fixed order.
+#include <math_constants.h>
+
+#include "rrv_common.cuh"
+
+namespace rrv {
+
+constexpr int ST_PIX = 2048;   // pixels per block
+
+__device__ __forceinline__ void atomic_min_double(double* a, double v) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(a);
+    unsigned long long old = *p;
+    while (__longlong_as_double((long long)old) > v) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+__device__ __forceinline__ void atomic_max_double(double* a, double v) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(a);
+    unsigned long long old = *p;
+    while (__longlong_as_double((long long)old) < v) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+
+__global__ void stats_init_kernel(double* part, int C, double count) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    part[c] = count;
+    part[C + c] = 0.0;
+    part[2 * C + c] = 0.0;
+    part[3 * C + c] = CUDART_INF;
+    part[4 * C + c] = -CUDART_INF;
+}
+
+// PASS 0: sum.  PASS 1: M2 about sum/count, min, max.
+template <int PASS>
+__global__ void __launch_bounds__(256) stats_kernel(const float* __restrict__ x, long long npix, int C, double* part) {
+    __shared__ double s_a[256];
+    __shared__ float s_mn[256], s_mx[256];
+    const int cpb = C < 256 ? C : 256;          // channels covered by one block
+    const int ppb = 256 / cpb;                  // pixel lanes per block
+    const int t = threadIdx.x;
+    const int cl = t % cpb, pl = t / cpb;
+    const int c = blockIdx.y * 256 + cl;
+    const bool active = pl < ppb && c < C;
+    const long long p0 = (long long)blockIdx.x * ST_PIX;
+    const long long p1 = p0 + ST_PIX < npix ? p0 + ST_PIX : npix;
+    double acc = 0.0;
+    float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+    if (active) {
+        if (PASS == 0) {
+            for (long long p = p0 + pl; p < p1; p += ppb) acc += (double)x[p * C + c];
+        } else {
+            const float mean = (float)(part[C + c] / part[c]);
+            for (long long p = p0 + pl; p < p1; p += ppb) {
+                const float v = x[p * C + c];
+                const float d = v - mean;          // fp32 like the reference's x - saved_mean
+                acc += (double)d * (double)d;
+                mn = fminf(mn, v);
+                mx = fmaxf(mx, v);
+            }
+        }
+    }
+    s_a[t] = acc; s_mn[t] = mn; s_mx[t] = mx;
+    __syncthreads();
+    if (pl == 0 && c < C) {
+        for (int k = 1; k < ppb; ++k) {
+            acc += s_a[k * cpb + cl];
+            mn = fminf(mn, s_mn[k * cpb + cl]);
+            mx = fmaxf(mx, s_mx[k * cpb + cl]);
+        }
+        if (PASS == 0) {
+            atomicAdd(part + C + c, acc);
+        } else {
+            atomicAdd(part + 2 * C + c, acc);
+            atomic_min_double(part + 3 * C + c, (double)mn);
+            atomic_max_double(part + 4 * C + c, (double)mx);
+        }
+    }
+}
+
+int channel_stats(const float* x, long long npix, int C, double* part, cudaStream_t st) {
+    RRV_REQUIRE(x && part, "rrv_channel_stats: NULL tensor");
+    RRV_REQUIRE(npix > 0 && C > 0, "rrv_channel_stats: empty tensor (npix=%lld C=%d)", npix, C);
+    RRV_REQUIRE(C <= 256 ? (256 % C == 0) : (C % 256 == 0), "rrv_channel_stats: C=%d must divide or be a multiple of 256", C);
+    stats_init_kernel<<<ceil_div(C, 256), 256, 0, st>>>(part, C, (double)npix);
+    if (check_launch("stats_init_kernel")) return 1;
+    dim3 grid(ceil_div(npix, ST_PIX), ceil_div(C, 256));
+    stats_kernel<0><<<grid, 256, 0, st>>>(x, npix, C, part);
+    if (check_launch("stats_kernel<0>")) return 1;
+    stats_kernel<1><<<grid, 256, 0, st>>>(x, npix, C, part);
+    return check_launch("stats_kernel<1>");
+}
+
+// Chan/Golub/LeVeque pairwise merge, applied left to right over the parts (deterministic).
+__global__ void stats_merge_kernel(const double* __restrict__ parts, int nparts, int C, double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double n = 0.0, sum = 0.0, m2 = 0.0, mn = CUDART_INF, mx = -CUDART_INF;
+    for (int k = 0; k < nparts; ++k) {
+        const double* p = parts + (long long)k * 5 * C;
+        const double nb = p[c];
+        if (nb <= 0.0) continue;
+        const double sb = p[C + c];
+        if (n == 0.0) {
+            n = nb; sum = sb; m2 = p[2 * C + c];
+        } else {
+            const double delta = sb / nb - sum / n;
+            m2 = m2 + p[2 * C + c] + delta * delta * n * nb / (n + nb);
+            n += nb; sum += sb;
+        }
+        mn = fmin(mn, p[3 * C + c]);
+        mx = fmax(mx, p[4 * C + c]);
+    }
+    out[c] = n; out[C + c] = sum; out[2 * C + c] = m2; out[3 * C + c] = mn; out[4 * C + c] = mx;
+}
+
+int stats_merge(const double* parts, int nparts, int C, double* merged, cudaStream_t st) {
+    RRV_REQUIRE(parts && merged && nparts > 0, "rrv_stats_merge: bad arguments");
+    stats_merge_kernel<<<ceil_div(C, 128), 128, 0, st>>>(parts, nparts, C, merged);
+    return check_launch("stats_merge_kernel");
+}
+
+__global__ void stats_finalize_kernel(const double* __restrict__ part, int C, int kind, float eps, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double n = part[c];
+    const float mean = (float)(part[C + c] / n);
+    if (kind == 2) { out[c] = mean; return; }
+    if (kind == 1) {
+        // EncoderStyle.cal_mean_std: sqrt(var_unbiased + eps), mean  -> AdaIN {scale, shift}
+        const float var = (float)(part[2 * C + c] / (n > 1.0 ? n - 1.0 : 1.0));
+        out[c] = sqrtf(var + eps);
+        out[C + c] = mean;
+        return;
+    }
+    // InstanceNorm.compute: rsqrt(mean((x-mean)^2) + eps); x_min / x_max of the normalised tensor.
+    // fp32 subtraction and multiplication are monotone, so max((x-m)*r) == (max(x)-m)*r bit for bit.
+    const float var = (float)(part[2 * C + c] / n);
+    const float rstd = 1.0f / sqrtf(var + eps);
+    out[c] = mean;
+    out[C + c] = rstd;
+    if (kind == 0) {
+        out[2 * C + c] = ((float)part[3 * C + c] - mean) * rstd;
+        out[3 * C + c] = ((float)part[4 * C + c] - mean) * rstd;
+    } else {
+        out[2 * C + c] = -CUDART_INF_F;
+        out[3 * C + c] = CUDART_INF_F;
+    }
+}
+
+int stats_finalize(const double* part, int C, int kind, float eps, float* out, cudaStream_t st) {
+    RRV_REQUIRE(part && out, "rrv_stats_finalize: NULL tensor");
+    RRV_REQUIRE(kind >= 0 && kind <= 3, "rrv_stats_finalize: bad kind %d", kind);
+    stats_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(part, C, kind, eps, out);
+    return check_launch("stats_finalize_kernel");
+}
+
+// FilterPredictor FC: out[j] = b[j] + sum_k W[j][k] * cat(c, s)[k]   (style_network_global.py:169)
+__global__ void filter_fc_kernel(const float* __restrict__ w, const float* __restrict__ b, const float* __restrict__ c_mean,
+                                 const float* __restrict__ s_mean, float* __restrict__ out) {
+    __shared__ float s_in[64];
+    if (threadIdx.x < 32) s_in[threadIdx.x] = c_mean[threadIdx.x];
+    else if (threadIdx.x < 64) s_in[threadIdx.x] = s_mean[threadIdx.x - 32];
+    __syncthreads();
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= 1024) return;
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) acc = fmaf(w[j * 64 + k], s_in[k], acc);
+    out[j] = acc + b[j];
+}
+
+int filter_fc(const float* w, const float* b, const float* c_mean, const float* s_mean, float* out, cudaStream_t st) {
+    RRV_REQUIRE(w && b && c_mean && s_mean && out, "rrv_filter_fc: NULL tensor");
+    filter_fc_kernel<<<8, 128, 0, st>>>(w, b, c_mean, s_mean, out);
+    return check_launch("filter_fc_kernel");
+}
+
+}  // namespace rrv

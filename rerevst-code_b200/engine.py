@@ -1,0 +1,434 @@
+"""Host-side orchestration of the CUDA path: weight repack, activation buffers and the launch
+sequences for the per-frame forward, the per-clip pre-pass and the per-style encoder.
+
+All arithmetic on activations happens in ``librerevst_b200.so`` (through the C ABI); torch is
+used for device memory, streams and one-off weight algebra (folding the predicted 32x32 dynamic
+filters into the neighbouring convolutions, see :meth:`StyleEngine._fold_filter`).
+
+Reference being replaced: ``test/style_network_global.py`` (Encoder :271-281, EncoderStyle
+:284-331, Decoder :334-451, TransformerNet :454-501).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from collections import namedtuple
+
+import torch
+
+from . import _lib as L
+from .weights import FILTERS, RES_BLOCKS, VGG_CONVS, VGG_POOL_AFTER, vgg_keys
+
+mean_std = namedtuple("mean_std", ["mean", "std"])
+vgg_outputs_super = namedtuple("VggOutputs", ["map", "relu1_1", "relu2_1", "relu3_1", "relu4_1"])
+
+STAT_NAMES = ("norm0", "norm1", "slice4.norm1", "slice4.norm2", "norm2", "slice3.norm1", "slice3.norm2",
+              "norm3", "slice2.norm1", "slice2.norm2", "norm4")
+INNER_PAD = 64          # the 32 KernelFilter channels are carried zero-padded to 64
+
+
+class Planes:
+    """NHWC activation as two 16-bit planes (hi = bf16(v), lo = 16-bit(v - hi)); lo is None in bf16 mode."""
+    __slots__ = ("hi", "lo", "N", "H", "W", "C")
+
+    def __init__(self, N, H, W, C, x3, device):
+        self.N, self.H, self.W, self.C = N, H, W, C
+        self.hi = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=device)
+        self.lo = torch.empty((N, H, W, C), dtype=torch.int16, device=device) if x3 else None
+
+    def slice0(self):
+        """View of batch item 0."""
+        p = Planes.__new__(Planes)
+        p.N, p.H, p.W, p.C = 1, self.H, self.W, self.C
+        p.hi = self.hi[:1]
+        p.lo = self.lo[:1] if self.lo is not None else None
+        return p
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+class ConvW:
+    """One convolution's weights in the layouts the kernels read, built once at load time
+    (SURVEY 8b item vi: state_dict -> kernel layout)."""
+
+    def __init__(self, w_oihw, bias, ups=False, cin_pad=None, cout_pad=None):
+        lib = L.lib()
+        w = w_oihw.detach().float().contiguous()
+        cout, cin, k, _ = w.shape
+        cin_p, cout_p = cin_pad or cin, cout_pad or cout
+        if (cin_p, cout_p) != (cin, cout):
+            wp = torch.zeros((cout_p, cin_p, k, k), dtype=torch.float32, device=w.device)
+            wp[:cout, :cin] = w
+            w = wp
+        self.Cin, self.Cout, self.ksize, self.ups = cin_p, cout_p, k, bool(ups)
+        self.bias = None
+        if bias is not None:
+            self.bias = torch.zeros(cout_p, dtype=torch.float32, device=w.device)
+            self.bias[:cout] = bias.detach().float()
+        co64 = 8 if cout_p < 8 else _round_up(cout_p, 64)
+        self.w_f32 = torch.empty((k * k, cin_p, co64), dtype=torch.float32, device=w.device)
+        L.check(lib.rrv_pack_weights_f32(w.data_ptr(), cin_p, cout_p, k, cin_p, co64, self.w_f32.data_ptr(), L.stream()),
+                "pack_weights_f32")
+        self.w_tc = None
+        nbytes = lib.rrv_tc_weight_bytes(cin_p, cout_p, k, int(self.ups))
+        if nbytes > 0:
+            self.w_tc = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+            L.check(lib.rrv_pack_weights_tc(w.data_ptr(), cin_p, cout_p, k, int(self.ups), self.w_tc.data_ptr(), L.stream()),
+                    "pack_weights_tc")
+        self._keep = w
+
+
+def make_epilogue(bias=None, act=0, norm1=None, res=None, res_shift=0, res_broadcast=False, norm2=None, affine=None):
+    e = L.Epilogue()
+    e.bias = L.ptr(bias)
+    e.act = act
+    e.norm1 = L.ptr(norm1)
+    if res is not None:
+        e.res_hi, e.res_lo = L.ptr(res.hi), L.ptr(res.lo)
+        e.res_shift, e.res_H, e.res_W = res_shift, res.H, res.W
+        e.res_batch_stride = 0 if res_broadcast else res.H * res.W * res.C
+    e.norm2 = L.ptr(norm2)
+    e.affine = L.ptr(affine)
+    e._keep = (bias, norm1, res, norm2, affine)
+    return e
+
+
+class StyleEngine:
+    """Everything ``TransformerNet`` needs on one GPU."""
+
+    def __init__(self, device, precision="x3", impl="auto"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("rerevst_b200 runs on CUDA devices only (there is no CPU path); got %s" % device)
+        self.lib = L.lib()
+        assert precision in ("x3", "bf16")
+        self.x3 = precision == "x3"
+        self.impl_name = impl
+        self.w = None
+        self.style = None            # dict: tables + map
+        self.F_style = None
+        self.stats = {}              # name -> float[4][C] table
+        self.filters = {}            # "Filter1" -> (wf1, wf2) fp32 [32,32]
+        self.fw = {}                 # "Filter1" -> (ConvW down', ConvW up')
+        self.samples = []
+        self.stats_allgather = None  # set by dist.ShardedPrepass: part[5,C] -> parts[G,5,C]
+        self._plans = {}
+        self.profile = None          # list -> (label, start_event, end_event, flops) per conv launch (bench.py)
+
+    # ------------------------------------------------------------------ weights
+    @property
+    def impl(self):
+        if self.impl_name == "ffma":
+            return L.IMPL_FFMA
+        if self.impl_name == "tc":
+            return L.IMPL_TCGEN05
+        return L.IMPL_TCGEN05 if self._have_tc else L.IMPL_FFMA
+
+    def load_weights(self, sd):
+        dev = self.device
+        g = lambda k: sd[k].detach().to(dev, torch.float32)
+        w = {}
+        for top in ("Encoder", "EncoderStyle"):
+            convs = []
+            for j, (wk, bk) in enumerate(vgg_keys(top)):
+                if j == 0:
+                    convs.append((g(wk).contiguous(), g(bk).contiguous()))     # conv1_1: rrv_first_layer
+                else:
+                    convs.append(ConvW(g(wk), g(bk)))
+            w[top] = convs
+        for name, cin, cout in RES_BLOCKS:
+            p = f"Decoder.{name}."
+            w[name] = dict(conv1=ConvW(g(p + "conv1.weight"), g(p + "conv1.bias"), ups=True),
+                           conv2=ConvW(g(p + "conv2.weight"), g(p + "conv2.bias")),
+                           short=ConvW(g(p + "conv_shortcut.weight"), None))
+        w["slice1"] = ConvW(g("Decoder.slice1.weight"), g("Decoder.slice1.bias"))
+        for f in FILTERS:
+            p = f"Decoder.{f}."
+            pred_w = torch.cat([g(p + "F1.down_sample.0.weight"), g(p + "F2.down_sample.0.weight")], 0)
+            pred_b = torch.cat([g(p + "F1.down_sample.0.bias"), g(p + "F2.down_sample.0.bias")], 0)
+            w[f] = dict(down_w=g(p + "down_sample.0.weight"), down_b=g(p + "down_sample.0.bias"),
+                        up_w=g(p + "upsample.0.weight"), up_b=g(p + "upsample.0.bias"),
+                        pred=ConvW(pred_w, pred_b),            # F1 | F2 predictor convs stacked: 512 -> 64
+                        fc=[(g(p + f"{q}.FC.weight").contiguous(), g(p + f"{q}.FC.bias").contiguous()) for q in ("F1", "F2")])
+        self.w = w
+        self._have_tc = w["slice1"].w_tc is not None
+        self.fw = {}
+        self._plans = {}
+        if self.filters:                       # re-fold cached filters against the new weights
+            for f, (a, b) in self.filters.items():
+                self._fold_filter(f, a, b)
+
+    # ------------------------------------------------------------------ thin wrappers over the C ABI
+    def _conv(self, cw, x, ep, out_mode=L.OUT_PLANES, out=None, N=None, out_C=0):
+        N = x.N if N is None else N
+        H, W = (x.H * 2, x.W * 2) if cw.ups else (x.H, x.W)
+        assert x.C == cw.Cin, (x.C, cw.Cin)
+        d = L.Conv()
+        d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = N, H, W, cw.Cin, cw.Cout, cw.ksize, int(cw.ups)
+        d.in_hi, d.in_lo = L.ptr(x.hi), L.ptr(x.lo)
+        d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
+        d.ep = ep
+        d.out_mode = out_mode
+        if out_mode == L.OUT_PLANES:
+            out = out or Planes(N, H, W, cw.Cout, self.x3, self.device)
+            d.out_hi, d.out_lo = L.ptr(out.hi), L.ptr(out.lo)
+        elif out_mode == L.OUT_F32_NHWC:
+            out = out if out is not None else torch.empty((N, H, W, cw.Cout), dtype=torch.float32, device=self.device)
+            d.out_f32 = out.data_ptr()
+        else:
+            out = out if out is not None else torch.empty((N, out_C, H, W), dtype=torch.float32, device=self.device)
+            d.out_f32, d.out_C = out.data_ptr(), out_C
+        if self.profile is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        L.check(self.lib.rrv_conv2d(C.byref(d), self.impl, L.stream()), "rrv_conv2d")
+        if self.profile is not None:
+            e1.record()
+            hin, win = x.H, x.W
+            self.profile.append((f"conv{cw.ksize}x{cw.ksize}{'u' if cw.ups else ''} {cw.Cin}->{cw.Cout} @{H}x{W}", e0, e1,
+                                 2.0 * cw.Cin * cw.Cout * cw.ksize * cw.ksize * N * H * W))
+        return out
+
+    def _pointwise(self, x_f32, ep, N=None, broadcast=False, to_f32=False):
+        n_in, H, W, Cc = x_f32.shape
+        N = n_in if N is None else N
+        bs = 0 if broadcast else H * W * Cc
+        if to_f32:
+            out = torch.empty((N, H, W, Cc), dtype=torch.float32, device=self.device)
+            L.check(self.lib.rrv_pointwise(x_f32.data_ptr(), bs, N, H, W, Cc, C.byref(ep), L.OUT_F32_NHWC, 0, 0,
+                                           out.data_ptr(), L.stream()), "rrv_pointwise")
+        else:
+            out = Planes(N, H, W, Cc, self.x3, self.device)
+            L.check(self.lib.rrv_pointwise(x_f32.data_ptr(), bs, N, H, W, Cc, C.byref(ep), L.OUT_PLANES, L.ptr(out.hi),
+                                           L.ptr(out.lo), 0, L.stream()), "rrv_pointwise")
+        return out
+
+    def _pool(self, x):
+        out = Planes(x.N, x.H // 2, x.W // 2, x.C, self.x3, self.device)
+        L.check(self.lib.rrv_maxpool2x2(L.ptr(x.hi), L.ptr(x.lo), x.N, x.H, x.W, x.C, L.ptr(out.hi), L.ptr(out.lo),
+                                        L.stream()), "rrv_maxpool2x2")
+        return out
+
+    def _stats_part(self, x_f32):
+        Cc = x_f32.shape[-1]
+        part = torch.empty((5, Cc), dtype=torch.float64, device=self.device)
+        L.check(self.lib.rrv_channel_stats(x_f32.data_ptr(), x_f32.numel() // Cc, Cc, part.data_ptr(), L.stream()),
+                "rrv_channel_stats")
+        if self.stats_allgather is not None:                      # frame-parallel pre-pass (dist.py)
+            parts = self.stats_allgather(part).contiguous()
+            merged = torch.empty_like(part)
+            L.check(self.lib.rrv_stats_merge(parts.data_ptr(), parts.shape[0], Cc, merged.data_ptr(), L.stream()),
+                    "rrv_stats_merge")
+            part = merged
+        return part
+
+    def _finalize(self, part, kind, eps):
+        Cc = part.shape[1]
+        rows = {0: 4, 1: 2, 2: 1, 3: 4}[kind]
+        out = torch.empty((rows, Cc), dtype=torch.float32, device=self.device)
+        L.check(self.lib.rrv_stats_finalize(part.data_ptr(), Cc, kind, eps, out.data_ptr(), L.stream()), "rrv_stats_finalize")
+        return out
+
+    def _saved_stat(self, x_f32):
+        """InstanceNorm.compute (style_network_global.py:59-77) -> float[4][C] table."""
+        return self._finalize(self._stats_part(x_f32), 0, 1e-8)
+
+    # ------------------------------------------------------------------ VGG stacks
+    def _vgg(self, top, src, kind, gray, N, H, W, mode, norm0=None):
+        """conv1_1 .. conv4_1.  mode 'content': planes of norm0(relu4_1); 'raw': fp32 NHWC relu4_1;
+        'style': dict of fp32 NHWC taps at relu1_1 / 2_1 / 3_1 / 4_1."""
+        convs = self.w[top]
+        w0, b0 = convs[0]
+        x = Planes(N, H, W, 64, self.x3, self.device)
+        taps = {}
+        f32 = torch.empty((N, H, W, 64), dtype=torch.float32, device=self.device) if mode == "style" else None
+        L.check(self.lib.rrv_first_layer(src.data_ptr(), kind, int(gray), N, H, W, w0.data_ptr(), b0.data_ptr(),
+                                         L.ptr(x.hi), L.ptr(x.lo), L.ptr(f32), L.stream()), "rrv_first_layer")
+        if mode == "style":
+            taps[0] = f32
+        ident = make_epilogue()
+        for (idx, _, _), cw in zip(VGG_CONVS[1:], convs[1:]):
+            last = idx == 19
+            ep = make_epilogue(bias=cw.bias, act=1)
+            if mode == "style" and idx in (5, 10, 19):
+                taps[idx] = self._conv(cw, x, ep, L.OUT_F32_NHWC)
+                if not last:
+                    x = self._pointwise(taps[idx], ident)
+            elif last and mode == "raw":
+                return self._conv(cw, x, ep, L.OUT_F32_NHWC)
+            elif last:
+                return self._conv(cw, x, make_epilogue(bias=cw.bias, act=1, norm1=norm0))
+            else:
+                x = self._conv(cw, x, ep)
+            if idx in VGG_POOL_AFTER:
+                x = self._pool(x)
+        return taps
+
+    # ------------------------------------------------------------------ style (once per style image)
+    @torch.no_grad()
+    def generate_style_features(self, style, kind=0):
+        """EncoderStyle.forward + cal_mean_std (style_network_global.py:304-331).
+        style: fp32 NCHW [1,3,h,w] normalised (kind 0) or uint8 HWC BGR [1,h,w,3] (kind 1)."""
+        if kind == 0:
+            N, _, H, W = style.shape
+        else:
+            N, H, W, _ = style.shape
+        assert N == 1
+        style = style.contiguous()
+        taps = self._vgg("EncoderStyle", style, kind, False, N, H, W, "style")
+        tabs = {}
+        for lvl, idx in (("relu1_1", 0), ("relu2_1", 5), ("relu3_1", 10), ("relu4_1", 19)):
+            x = taps[idx]
+            Cc = x.shape[-1]
+            part = torch.empty((5, Cc), dtype=torch.float64, device=self.device)
+            L.check(self.lib.rrv_channel_stats(x.data_ptr(), x.numel() // Cc, Cc, part.data_ptr(), L.stream()), "stats")
+            tabs[lvl] = self._finalize(part, 1, 1e-5)          # float[2][C] = {std, mean} = AdaIN {scale, shift}
+        smap = taps[19]                                       # [1, h/8, w/8, 512] fp32
+        # normalized_style = (map - mean) / std  (:371, :397), carried as planes for the predictor convs
+        sc, sh = tabs["relu4_1"][0], tabs["relu4_1"][1]
+        ntab = torch.stack([sh, 1.0 / sc, torch.full_like(sc, float("-inf")), torch.full_like(sc, float("inf"))]).contiguous()
+        nstyle = self._pointwise(smap, make_epilogue(norm1=ntab))
+        self.style = dict(tabs=tabs, map=smap, nstyle=nstyle)
+        ms = {k: mean_std(v[1].view(1, -1, 1, 1), v[0].view(1, -1, 1, 1)) for k, v in tabs.items()}
+        self.F_style = vgg_outputs_super(smap.permute(0, 3, 1, 2), ms["relu1_1"], ms["relu2_1"], ms["relu3_1"], ms["relu4_1"])
+        self._plans = {}
+
+    # ------------------------------------------------------------------ pre-pass
+    def clean(self):
+        self.samples = []
+        self.stats = {}
+        self.filters = {}
+        self.fw = {}
+        self._plans = {}
+
+    @torch.no_grad()
+    def add(self, patch, kind=0):
+        """TransformerNet.add (:471-475): Encoder(RGB2Gray(patch)) kept for compute()."""
+        if kind == 0:
+            N, _, H, W = patch.shape
+        else:
+            N, H, W, _ = patch.shape
+        self.samples.append(self._vgg("Encoder", patch.contiguous(), kind, True, N, H, W, "raw"))
+
+    def _fold_filter(self, f, wf1, wf2):
+        """Fold the two predicted 32x32 matrices of a KernelFilter (apply_filter, :194-217) into its
+        down_sample / upsample convolutions: Wf1 . conv_down(x) == conv_{Wf1.Wdown}(x) and
+        conv_up(Wf2 . t) == conv_{Wup.Wf2}(t).  One-off per clip, fp32."""
+        fw = self.w[f]
+        dw = torch.matmul(wf1, fw["down_w"].reshape(32, -1)).reshape(32, 512, 3, 3)
+        db = torch.mv(wf1, fw["down_b"])
+        uw = torch.einsum("ojyx,ji->oiyx", fw["up_w"], wf2).contiguous()
+        self.fw[f] = (ConvW(dw, db, cout_pad=INNER_PAD), ConvW(uw, fw["up_b"], cin_pad=INNER_PAD))
+        self.filters[f] = (wf1, wf2)
+
+    def _predict_filters(self, f, content):
+        """FilterPredictor.compute for F1 and F2 of one KernelFilter (:161-172): both predictor convs
+        run as one 512 -> 64 convolution; spatial+batch mean; Linear(64 -> 1024) each."""
+        fw = self.w[f]
+        ep = make_epilogue(bias=fw["pred"].bias)
+        c_mean = self._finalize(self._stats_part(self._conv(fw["pred"], content, ep, L.OUT_F32_NHWC)), 2, 0.0)[0]
+        s = self._conv(fw["pred"], self.style["nstyle"], ep, L.OUT_F32_NHWC)
+        part = torch.empty((5, 64), dtype=torch.float64, device=self.device)
+        L.check(self.lib.rrv_channel_stats(s.data_ptr(), s.numel() // 64, 64, part.data_ptr(), L.stream()), "stats")
+        s_mean = self._finalize(part, 2, 0.0)[0]
+        out = []
+        for j, (fcw, fcb) in enumerate(fw["fc"]):
+            wf = torch.empty((32, 32), dtype=torch.float32, device=self.device)
+            L.check(self.lib.rrv_filter_fc(fcw.data_ptr(), fcb.data_ptr(), c_mean[32 * j:].data_ptr(),
+                                           s_mean[32 * j:].data_ptr(), wf.data_ptr(), L.stream()), "rrv_filter_fc")
+            out.append(wf)
+        return out
+
+    @torch.no_grad()
+    def compute(self):
+        """Decoder.compute (:425-439): 11 global statistic tables + 6 dynamic filters, stage by stage
+        over all sampled frames.  Quirk Q1 is reproduced: only sample 0 goes through the dynamic
+        filters and its residual is broadcast to every sample."""
+        if self.style is None:
+            raise RuntimeError("compute() before generate_style_features()")
+        if not self.samples:
+            raise RuntimeError("compute() without add(): no sampled frames")
+        x = torch.cat(self.samples, 0) if len(self.samples) > 1 else self.samples[0]
+        N = x.shape[0]
+        st = self.stats
+        tabs = self.style["tabs"]
+        st["norm0"] = self._saved_stat(x)
+        h = self._pointwise(x, make_epilogue(norm1=st["norm0"]))            # planes [N, h, w, 512]
+        del x
+        for i, f in enumerate(FILTERS):
+            wf1, wf2 = self._predict_filters(f, h)
+            self._fold_filter(f, wf1, wf2)
+            down, up = self.fw[f]
+            t = self._conv(down, h.slice0(), make_epilogue(bias=down.bias, act=2))
+            u0 = self._conv(up, t, make_epilogue(bias=up.bias), L.OUT_F32_NHWC)   # [1,h,w,512]
+            if i < 2:
+                h = self._pointwise(u0, make_epilogue(res=h), N=N, broadcast=True)
+            else:
+                r = self._pointwise(u0, make_epilogue(res=h), N=N, broadcast=True, to_f32=True)
+        levels = (("norm1", "relu4_1", "slice4"), ("norm2", "relu3_1", "slice3"),
+                  ("norm3", "relu2_1", "slice2"), ("norm4", "relu1_1", None))
+        for nname, lvl, block in levels:
+            st[nname] = self._saved_stat(r)
+            if block is None:
+                break
+            h = self._pointwise(r, make_epilogue(norm1=st[nname], affine=tabs[lvl]))
+            del r
+            bw = self.w[block]
+            s = self._conv(bw["short"], h, make_epilogue())
+            r1 = self._conv(bw["conv1"], h, make_epilogue(bias=bw["conv1"].bias, act=2), L.OUT_F32_NHWC)
+            st[block + ".norm1"] = self._saved_stat(r1)
+            h = self._pointwise(r1, make_epilogue(norm1=st[block + ".norm1"]))
+            del r1
+            r2 = self._conv(bw["conv2"], h, make_epilogue(bias=bw["conv2"].bias, act=2), L.OUT_F32_NHWC)
+            st[block + ".norm2"] = self._saved_stat(r2)
+            r = self._pointwise(r2, make_epilogue(norm1=st[block + ".norm2"], res=s, res_shift=1), to_f32=True)
+            del r2
+        self.samples = []
+        self._plans = {}
+
+    # ------------------------------------------------------------------ per-frame forward
+    def _require_ready(self):
+        if self.style is None:
+            raise RuntimeError("forward() before generate_style_features()")
+        if len(self.stats) != len(STAT_NAMES) or len(self.fw) != 3:
+            raise RuntimeError("forward() before compute(): the global statistics are not available "
+                               "(the reference fails here with AttributeError: 'NoneType' has no attribute 'expand')")
+
+    @torch.no_grad()
+    def forward(self, frame, kind=0, out=None):
+        """TransformerNet.forward (:499-501) for a batch of independent frames.
+        frame: fp32 NCHW normalised (kind 0) or uint8 NHWC BGR (kind 1).  Returns fp32 NCHW."""
+        self._require_ready()
+        if kind == 0:
+            N, _, H, W = frame.shape
+        else:
+            N, H, W, _ = frame.shape
+        st, tabs = self.stats, self.style["tabs"]
+        h = self._vgg("Encoder", frame.contiguous(), kind, True, N, H, W, "content", norm0=st["norm0"])
+        for i, f in enumerate(FILTERS):
+            down, up = self.fw[f]
+            t = self._conv(down, h, make_epilogue(bias=down.bias, act=2))
+            if i < 2:
+                h = self._conv(up, t, make_epilogue(bias=up.bias, res=h))
+            else:   # + Decoder.norm[1] and AdaIN(relu4_1) (:443)
+                h = self._conv(up, t, make_epilogue(bias=up.bias, res=h, norm2=st["norm1"], affine=tabs["relu4_1"]))
+        for block, nxt, lvl in (("slice4", "norm2", "relu3_1"), ("slice3", "norm3", "relu2_1"), ("slice2", "norm4", "relu1_1")):
+            bw = self.w[block]
+            s = self._conv(bw["short"], h, make_epilogue())                 # 1x1 shortcut at low resolution
+            y = self._conv(bw["conv1"], h, make_epilogue(bias=bw["conv1"].bias, act=2, norm1=st[block + ".norm1"]))
+            h = self._conv(bw["conv2"], y, make_epilogue(bias=bw["conv2"].bias, act=2, norm1=st[block + ".norm2"],
+                                                        res=s, res_shift=1, norm2=st[nxt], affine=tabs[lvl]))
+        head = self.w["slice1"]
+        return self._conv(head, h, make_epilogue(bias=head.bias), L.OUT_F32_NCHW, out=out, out_C=3)
+
+    # ------------------------------------------------------------------ state export (tests, dist)
+    def export_clip_state(self):
+        return dict(stats={k: v.clone() for k, v in self.stats.items()},
+                    filters={k: (a.clone(), b.clone()) for k, (a, b) in self.filters.items()})
+
+    def import_clip_state(self, state):
+        self.stats = {k: v.to(self.device).contiguous() for k, v in state["stats"].items()}
+        for f, (a, b) in state["filters"].items():
+            self._fold_filter(f, a.to(self.device), b.to(self.device))
+        self._plans = {}

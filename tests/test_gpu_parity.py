@@ -1,0 +1,377 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the golden
+fixtures of the unmodified reference.  Tolerances follow BASELINE.json: <= 1e-3 relative L-inf
+for the fp32-accurate ("x3") path, exact equality for the warp's integer indices."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, rel_linf
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3          # north_star: 1e-3 relative L-inf (fp32)
+TIGHT = 2e-5        # single fp32 layers (FFMA path: operands carry >= 16 mantissa bits)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def L():
+    from rerevst_code_b200 import _lib
+    _lib.lib()
+    return _lib
+
+
+def _impls(L):
+    out = [("ffma", L.IMPL_FFMA)]
+    if L.lib().rrv_tc_weight_bytes(64, 64, 3, 0) > 0:
+        out.append(("tc", L.IMPL_TCGEN05))
+    return out
+
+
+def _to_planes(L, x_nchw, x3=True):
+    from rerevst_code_b200.engine import Planes
+    N, Cc, H, W = x_nchw.shape
+    p = Planes(N, H, W, Cc, x3, x_nchw.device)
+    L.check(L.lib().rrv_nchw_to_planes(x_nchw.contiguous().data_ptr(), N, H, W, Cc, L.ptr(p.hi), L.ptr(p.lo), L.stream()))
+    return p
+
+
+def _from_planes(L, p):
+    out = torch.empty((p.N, p.C, p.H, p.W), dtype=torch.float32, device=p.hi.device)
+    L.check(L.lib().rrv_planes_to_nchw(L.ptr(p.hi), L.ptr(p.lo), p.N, p.H, p.W, p.C, out.data_ptr(), L.stream()))
+    return out
+
+
+def test_native_library_is_loaded_in_tree(L):
+    maps = open("/proc/self/maps").read()
+    assert "rerevst-code_b200/csrc/librerevst_b200.so" in maps
+
+
+def test_planes_roundtrip_keeps_16_bits(L, dev):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 16, 9, 11, generator=g)
+    for fmt, bits in ((0, 2.0 ** -16), (1, 2.0 ** -18)):
+        L.check(L.lib().rrv_set_lo_format(fmt))
+        y = _from_planes(L, _to_planes(L, x.to(dev))).cpu()
+        assert float(((y - x).abs() / x.abs().clamp_min(0.05)).max()) < bits
+    L.check(L.lib().rrv_set_lo_format(0))
+
+
+# ---------------------------------------------------------------------------------- single layers
+
+CONV_CASES = [
+    # N, H, W, Cin, Cout, k, ups
+    (1, 16, 16, 64, 64, 3, 0),
+    (2, 24, 40, 64, 128, 3, 0),
+    (1, 13, 19, 128, 64, 3, 0),          # ragged: not a multiple of any tile
+    (1, 16, 32, 256, 128, 3, 1),         # nearest x2 folded into the gather
+    (1, 12, 20, 512, 256, 1, 0),         # 1x1 shortcut
+    (1, 9, 150, 64, 64, 3, 0),           # wider than one row tile
+    (1, 40, 8, 128, 512, 3, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_matches_torch_cpu(L, dev, case):
+    from rerevst_code_b200.engine import ConvW, make_epilogue
+    N, H, W, Cin, Cout, k, ups = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    hin, win = (H // 2, W // 2) if ups else (H, W)
+    x = torch.randn(N, Cin, hin, win, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    xin = F.interpolate(x, scale_factor=2, mode="nearest") if ups else x
+    ref = F.leaky_relu(F.conv2d(xin, w, b, padding=k // 2), 0.2)
+    cw = ConvW(w.to(dev), b.to(dev), ups=bool(ups))
+    xp = _to_planes(L, x.to(dev))
+    xq = _from_planes(L, xp).cpu()                     # what the kernel really sees (16+ bit operands)
+    xin_q = F.interpolate(xq, scale_factor=2, mode="nearest") if ups else xq
+    ref_q = F.leaky_relu(F.conv2d(xin_q, w, b, padding=k // 2), 0.2)
+    for name, impl in _impls(L):
+        d = L.Conv()
+        d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = N, H, W, Cin, Cout, k, ups
+        d.in_hi, d.in_lo = L.ptr(xp.hi), L.ptr(xp.lo)
+        d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
+        d.ep = make_epilogue(bias=cw.bias, act=2)
+        d.out_mode = L.OUT_F32_NHWC
+        out = torch.empty((N, H, W, Cout), dtype=torch.float32, device=dev)
+        d.out_f32 = out.data_ptr()
+        L.check(L.lib().rrv_conv2d(C.byref(d), impl, L.stream()), name)
+        got = out.permute(0, 3, 1, 2).cpu()
+        assert rel_linf(got, ref_q) < (TIGHT if name == "ffma" else 2e-4), name
+        assert rel_linf(got, ref) < 2e-4, name
+
+
+def test_conv_full_epilogue_chain(L, dev):
+    """bias -> LeakyReLU -> saved-stat norm -> + half-res residual -> saved-stat norm -> AdaIN."""
+    from rerevst_code_b200.engine import ConvW, make_epilogue
+    from oracle import stylenet
+    g = torch.Generator().manual_seed(11)
+    N, H, W, Cc = 2, 16, 24, 64
+    x = torch.randn(N, Cc, H, W, generator=g)
+    w = torch.randn(Cc, Cc, 3, 3, generator=g) / 24.0
+    b = torch.randn(Cc, generator=g) * 0.1
+    res = torch.randn(N, Cc, H // 2, W // 2, generator=g)
+    y = F.leaky_relu(F.conv2d(x, w, b, padding=1), 0.2)
+    st1, _ = stylenet.in_compute(y)
+    # clamp tighter than the data so the max/min stages are exercised
+    st1 = stylenet.SavedStat(st1.mean, st1.rstd, st1.lo * 0.5, st1.hi * 0.5)
+    y1 = stylenet.in_forward(y, st1) + F.interpolate(res, scale_factor=2, mode="nearest")
+    st2, _ = stylenet.in_compute(y1)
+    st2 = stylenet.SavedStat(st2.mean, st2.rstd, st2.lo * 0.7, st2.hi * 0.7)
+    sc, sh = torch.rand(Cc, generator=g) + 0.5, torch.randn(Cc, generator=g)
+    ref = stylenet.in_forward(y1, st2) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
+    tab = lambda s: torch.stack([t.reshape(-1) for t in s]).contiguous().to(dev)
+    cw = ConvW(w.to(dev), b.to(dev))
+    xp, rp = _to_planes(L, x.to(dev)), _to_planes(L, res.to(dev))
+    t1, t2, aff = tab(st1), tab(st2), torch.stack([sc, sh]).contiguous().to(dev)
+    for name, impl in _impls(L):
+        d = L.Conv()
+        d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = N, H, W, Cc, Cc, 3, 0
+        d.in_hi, d.in_lo = L.ptr(xp.hi), L.ptr(xp.lo)
+        d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
+        d.ep = make_epilogue(bias=cw.bias, act=2, norm1=t1, res=rp, res_shift=1, norm2=t2, affine=aff)
+        from rerevst_code_b200.engine import Planes
+        o = Planes(N, H, W, Cc, True, dev)
+        d.out_mode, d.out_hi, d.out_lo = L.OUT_PLANES, L.ptr(o.hi), L.ptr(o.lo)
+        L.check(L.lib().rrv_conv2d(C.byref(d), impl, L.stream()), name)
+        assert rel_linf(_from_planes(L, o).cpu(), ref) < 3e-4, name
+
+
+@pytest.mark.parametrize("kind,gray", [(0, 1), (0, 0), (1, 1), (1, 0)])
+def test_first_layer_matches_oracle(L, dev, state_dict, kind, gray):
+    from oracle import stylenet
+    g = torch.Generator().manual_seed(5)
+    H, W = 37, 53
+    w, b = state_dict["Encoder.slice.0.weight"], state_dict["Encoder.slice.0.bias"]
+    if kind == 0:
+        x = torch.randn(2, 3, H, W, generator=g)
+        src = x.to(dev)
+    else:
+        u8 = torch.randint(0, 256, (2, H, W, 3), generator=g, dtype=torch.uint8)
+        x = torch.cat([stylenet.transform_image(stylenet.numpy2tensor(u8[i].numpy())) for i in range(2)], 0)
+        src = u8.to(dev)
+    xin = stylenet.rgb2gray(x) if gray else x
+    ref = F.relu(F.conv2d(xin, w, b, padding=1))
+    out = torch.empty((2, H, W, 64), dtype=torch.float32, device=dev)
+    L.check(L.lib().rrv_first_layer(src.data_ptr(), kind, gray, 2, H, W, w.to(dev).data_ptr(), b.to(dev).data_ptr(),
+                                    0, 0, out.data_ptr(), L.stream()))
+    assert rel_linf(out.permute(0, 3, 1, 2).cpu(), ref) < TIGHT
+
+
+def test_maxpool_matches_torch(L, dev):
+    from rerevst_code_b200.engine import Planes
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 64, 13, 18, generator=g)       # odd height: floor like nn.MaxPool2d
+    xp = _to_planes(L, x.to(dev))
+    xq = _from_planes(L, xp).cpu()
+    o = Planes(2, 6, 9, 64, True, dev)
+    L.check(L.lib().rrv_maxpool2x2(L.ptr(xp.hi), L.ptr(xp.lo), 2, 13, 18, 64, L.ptr(o.hi), L.ptr(o.lo), L.stream()))
+    assert torch.equal(_from_planes(L, o).cpu(), F.max_pool2d(xq, 2, 2))
+
+
+@pytest.mark.parametrize("shape", [(3, 10, 12, 64), (2, 7, 9, 512), (1, 64, 64, 128), (5, 3, 3, 256)])
+def test_saved_stat_tables_match_instance_norm_compute(L, dev, shape):
+    from oracle import stylenet
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(*shape, generator=g) * 3 + 1.5           # NHWC
+    st, _ = stylenet.in_compute(x.permute(0, 3, 1, 2))
+    ref = torch.stack([t.reshape(-1) for t in st])
+    Cc = shape[-1]
+    xd = x.to(dev).contiguous()
+    part = torch.empty((5, Cc), dtype=torch.float64, device=dev)
+    out = torch.empty((4, Cc), dtype=torch.float32, device=dev)
+    L.check(L.lib().rrv_channel_stats(xd.data_ptr(), xd.numel() // Cc, Cc, part.data_ptr(), L.stream()))
+    L.check(L.lib().rrv_stats_finalize(part.data_ptr(), Cc, 0, 1e-8, out.data_ptr(), L.stream()))
+    got = out.cpu()
+    for r in range(4):
+        assert rel_linf(got[r], ref[r]) < 1e-5, r
+    # unbiased mean/std of EncoderStyle.cal_mean_std on the first sample
+    ms = stylenet.cal_mean_std(x[:1].permute(0, 3, 1, 2))
+    x1 = xd[:1].contiguous()
+    L.check(L.lib().rrv_channel_stats(x1.data_ptr(), x1.numel() // Cc, Cc, part.data_ptr(), L.stream()))
+    out2 = torch.empty((2, Cc), dtype=torch.float32, device=dev)
+    L.check(L.lib().rrv_stats_finalize(part.data_ptr(), Cc, 1, 1e-5, out2.data_ptr(), L.stream()))
+    assert rel_linf(out2[0].cpu(), ms.std.reshape(-1)) < 1e-5 and rel_linf(out2[1].cpu(), ms.mean.reshape(-1)) < 1e-5
+
+
+def test_stats_merge_equals_single_pass(L, dev):
+    """Sharded pre-pass: per-rank partials merged with Chan's formula == statistics of the whole batch."""
+    g = torch.Generator().manual_seed(4)
+    x = (torch.randn(6, 8, 8, 128, generator=g) * 2 + 0.3).to(dev)
+    Cc = 128
+    whole = torch.empty((5, Cc), dtype=torch.float64, device=dev)
+    L.check(L.lib().rrv_channel_stats(x.data_ptr(), x.numel() // Cc, Cc, whole.data_ptr(), L.stream()))
+    parts = torch.empty((3, 5, Cc), dtype=torch.float64, device=dev)
+    for i, (a, b) in enumerate(((0, 1), (1, 4), (4, 6))):
+        xs = x[a:b].contiguous()
+        L.check(L.lib().rrv_channel_stats(xs.data_ptr(), xs.numel() // Cc, Cc, parts[i].data_ptr(), L.stream()))
+    merged = torch.empty_like(whole)
+    L.check(L.lib().rrv_stats_merge(parts.data_ptr(), 3, Cc, merged.data_ptr(), L.stream()))
+    assert torch.equal(merged[0], whole[0]) and torch.equal(merged[3:], whole[3:])
+    assert torch.allclose(merged[1], whole[1], rtol=1e-12) and torch.allclose(merged[2], whole[2], rtol=1e-9)
+
+
+# ---------------------------------------------------------------------------------- whole path
+
+def _run_cuda_global(name, state_dict, dev, precision="x3", impl="auto"):
+    from oracle import cases
+    from rerevst_code_b200.style_network_global import TransformerNet
+    style, samples, frame = cases.global_inputs(name)
+    net = TransformerNet(precision=precision, impl=impl).to(dev)
+    net.load_state_dict(state_dict)
+    net.generate_style_features(style.to(dev))
+    net.clean()
+    for s in samples:
+        net.add(s.to(dev))
+    net.compute()
+    out = net(frame.to(dev))
+    return net, out
+
+
+@pytest.mark.parametrize("impl", ["ffma", "tc"])
+@pytest.mark.parametrize("name", ["small_q3", "n1", "cfg1_256"])
+def test_global_mode_matches_reference_golden(L, dev, state_dict, name, impl):
+    if impl == "tc" and len(_impls(L)) < 2:
+        pytest.skip("tcgen05 path not built")
+    gold = np.load(os.path.join(GOLDEN, f"global_{name}.npz"))
+    net, out = _run_cuda_global(name, state_dict, dev, impl=impl)
+    eng = net._engine
+    for lvl in ("relu1_1", "relu2_1", "relu3_1", "relu4_1"):
+        tab = eng.style["tabs"][lvl].cpu().numpy()            # {std, mean}
+        assert rel_linf(tab[1], gold[f"style/{lvl}"][0]) < TOL and rel_linf(tab[0], gold[f"style/{lvl}"][1]) < TOL
+    for k in eng.stats:
+        got = eng.stats[k].cpu().numpy()
+        for r in range(4):
+            assert rel_linf(got[r], gold["stat/" + k][r]) < TOL, (k, r)
+    for f in ("Filter1", "Filter2", "Filter3"):
+        for j, p in enumerate(("F1", "F2")):
+            assert rel_linf(eng.filters[f][j].cpu().numpy(), gold[f"filter/{f}.{p}"]) < TOL, (f, p)
+    assert tuple(out.shape) == gold["out"].shape
+    assert rel_linf(out.cpu().numpy(), gold["out"]) < TOL
+
+
+def test_forward_with_oracle_statistics(L, dev, state_dict):
+    """Per-frame forward alone: clip state imported from the oracle, so only forward error counts."""
+    from oracle import cases, stylenet
+    from rerevst_code_b200.style_network_global import TransformerNet
+    style, samples, frame = cases.global_inputs("small_q3")
+    o = stylenet.GlobalOracle(state_dict)
+    o.generate_style_features(style)
+    o.clean()
+    for s in samples:
+        o.add(s)
+    o.compute()
+    ref = o.forward(frame)
+    net = TransformerNet().to(dev)
+    net.load_state_dict(state_dict)
+    net.generate_style_features(style.to(dev))
+    eng = net._engine
+    stats = {k: torch.stack([t.reshape(-1) for t in v]).contiguous() for k, v in o.clip.stats.items()}
+    filters = {k: (a.reshape(32, 32).contiguous(), b.reshape(32, 32).contiguous()) for k, (a, b) in o.clip.filters.items()}
+    eng.import_clip_state(dict(stats=stats, filters=filters))
+    for impl in [n for n, _ in _impls(L)]:
+        eng.impl_name = impl
+        assert rel_linf(net(frame.to(dev)).cpu(), ref) < TOL, impl
+    # Q2: a batch of frames == independent B=1 forwards
+    eng.impl_name = "auto"
+    g = torch.Generator().manual_seed(8)
+    f2 = torch.randn(1, 3, 64, 96, generator=g)
+    both = net(torch.cat([frame, f2]).to(dev)).cpu()
+    assert rel_linf(both[:1], ref) < TOL and rel_linf(both[1:], o.forward(f2)) < TOL
+
+
+def test_forward_before_compute_raises(dev, state_dict):
+    from rerevst_code_b200.style_network_global import TransformerNet
+    net = TransformerNet().to(dev)
+    net.load_state_dict(state_dict)
+    net.generate_style_features(torch.zeros(1, 3, 32, 32, device=dev))
+    net.clean()
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 32, 32, device=dev))
+
+
+def test_stylization_facade_u8_path(L, dev, state_dict):
+    """framework.Stylization: uint8 BGR in, float32 BGR [0,255] out, incl. the script's crop."""
+    from oracle import stylenet
+    from rerevst_code_b200.framework import Stylization
+    rng = np.random.RandomState(0)
+    smooth = lambda h, w: np.clip(rng.rand(h // 8 + 1, w // 8 + 1, 3).repeat(8, 0).repeat(8, 1)[:h, :w] * 255, 0, 255).astype(np.uint8)
+    style, f0, f1, frame = smooth(64, 72), smooth(48, 64), smooth(48, 64), smooth(64, 96)
+    o = stylenet.GlobalOracle(state_dict)
+    o.generate_style_features(stylenet.transform_image(stylenet.numpy2tensor(style)))
+    o.clean()
+    for f in (f0, f1):
+        o.add(stylenet.transform_image(stylenet.numpy2tensor(f)))
+    o.compute()
+    ref = o.transfer(frame)
+    fw = Stylization(state_dict, cuda=True)
+    fw.prepare_style(style)
+    fw.clean()
+    fw.add(f0)
+    fw.add(f1)
+    fw.compute()
+    got = fw.transfer(frame)
+    assert got.dtype == np.float32 and got.shape == ref.shape
+    assert float(np.max(np.abs(got - ref))) < 255 * TOL
+    crop = fw.transfer(frame, crop=(8, 16, 40, 64))
+    assert np.array_equal(crop, got[8:48, 16:80])
+
+
+# ---------------------------------------------------------------------------------- warp
+
+def _index_image(b, h, w):
+    img = np.zeros((b, 2, h, w), np.float32)
+    img[:, 0] = np.arange(w, dtype=np.float32)[None, None, :]
+    img[:, 1] = np.arange(h, dtype=np.float32)[None, :, None]
+    return img
+
+
+def test_warp_indices_bit_exact(dev):
+    from oracle import cases, warp as ow
+    from rerevst_code_b200.loss_networks import warp, warp_indices
+    with open(os.path.join(GOLDEN, "warp_digests.json")) as f:
+        digests = json.load(f)
+    for (h, w) in cases.WARP_SIZES + cases.WARP_SMALL:
+        flo = cases.warp_flow(h, w)
+        idx = warp_indices(torch.from_numpy(flo).to(dev)).cpu().numpy()
+        iy, ix = ow.warp_indices(flo)
+        assert np.array_equal(idx[..., 0], iy) and np.array_equal(idx[..., 1], ix), (h, w)
+        assert cases.digest(idx[..., 1].astype(np.int32)) == digests[f"{h}x{w}"]["ix_sha256"]
+        assert cases.digest(idx[..., 0].astype(np.int32)) == digests[f"{h}x{w}"]["iy_sha256"]
+        img = _index_image(flo.shape[0], h, w)
+        out = warp(torch.from_numpy(img).to(dev), torch.from_numpy(flo).to(dev)).cpu().numpy()
+        assert np.array_equal(out, ow.warp(img, flo))
+
+
+def test_temporal_loss_and_backward(dev):
+    from oracle import cases, warp as ow
+    from rerevst_code_b200.loss_networks import TemporalLoss, warp
+    gold = np.load(os.path.join(GOLDEN, "warp.npz"))
+    g = torch.Generator().manual_seed(99)
+    first = torch.randn(2, 3, 64, 64, generator=g)
+    second = torch.randn(2, 3, 64, 64, generator=g)
+    flo = torch.from_numpy(cases.warp_flow(64, 64))
+    loss, warped = TemporalLoss()(first.to(dev), second.to(dev), flo.to(dev))
+    assert np.array_equal(warped.cpu().numpy(), gold["tl/warped"])
+    assert abs(float(loss) - float(gold["tl/loss"])) <= 1e-6 * float(gold["tl/loss"])
+    # backward: scatter-add of the output gradient to the source pixels
+    x = first.to(dev).requires_grad_(True)
+    go = torch.randn(2, 3, 64, 64, generator=g)
+    warp(x, flo.to(dev)).backward(go.to(dev))
+    iy, ix = ow.warp_indices(flo.numpy())
+    ref = np.zeros((2, 3, 64, 64), np.float64)
+    for b in range(2):
+        for c in range(3):
+            np.add.at(ref[b, c], (iy[b], ix[b]), go[b, c].numpy().astype(np.float64))
+    assert rel_linf(x.grad.cpu().numpy(), ref) < 1e-5
