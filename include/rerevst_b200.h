@@ -90,6 +90,9 @@ int rrv_conv2d(const rrv_conv* p, int impl, void* stream);
  * w_oihw: fp32 [Cout][Cin][k][k] (PyTorch layout) on the device. */
 int64_t rrv_tc_weight_bytes(int Cin, int Cout, int ksize, int ups);
 int rrv_pack_weights_tc(const float* w_oihw, int Cin, int Cout, int ksize, int ups, void* blob, void* stream);
+/* Tuning knobs of the tensor-core kernel (defaults 256, 16, 6): widest Cout tile, width of the
+ * 128-pixel spatial tile (8..128, power of two), deepest shared-memory pipeline. */
+int rrv_tc_tune(int max_bn, int tile_w, int max_stages);
 /* fp32 [Cout][Cin][k][k] -> [k*k][Cin_pad][Cout_pad] fp32 (zero padded) for the FFMA path. */
 int rrv_pack_weights_f32(const float* w_oihw, int Cin, int Cout, int ksize, int Cin_pad, int Cout_pad,
                          float* out, void* stream);

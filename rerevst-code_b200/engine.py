@@ -119,11 +119,17 @@ class StyleEngine:
     # ------------------------------------------------------------------ weights
     @property
     def impl(self):
+        """Kernel family of the per-frame convolutions: the tcgen05 implicit GEMM unless 'ffma' is forced."""
+        return L.IMPL_FFMA if self.impl_name == "ffma" else L.IMPL_TCGEN05
+
+    def _impl_for(self, cw):
         if self.impl_name == "ffma":
             return L.IMPL_FFMA
-        if self.impl_name == "tc":
-            return L.IMPL_TCGEN05
-        return L.IMPL_TCGEN05 if self._have_tc else L.IMPL_FFMA
+        if cw.w_tc is None:
+            if self.impl_name == "tc":
+                raise RuntimeError(f"no tensor-core kernel for conv {cw.Cin}->{cw.Cout} k={cw.ksize}")
+            return L.IMPL_FFMA
+        return L.IMPL_TCGEN05
 
     def load_weights(self, sd):
         dev = self.device
@@ -152,7 +158,6 @@ class StyleEngine:
                         pred=ConvW(pred_w, pred_b),            # F1 | F2 predictor convs stacked: 512 -> 64
                         fc=[(g(p + f"{q}.FC.weight").contiguous(), g(p + f"{q}.FC.bias").contiguous()) for q in ("F1", "F2")])
         self.w = w
-        self._have_tc = w["slice1"].w_tc is not None
         self.fw = {}
         self._plans = {}
         if self.filters:                       # re-fold cached filters against the new weights
@@ -182,7 +187,7 @@ class StyleEngine:
         if self.profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        L.check(self.lib.rrv_conv2d(C.byref(d), self.impl, L.stream()), "rrv_conv2d")
+        L.check(self.lib.rrv_conv2d(C.byref(d), self._impl_for(cw), L.stream()), "rrv_conv2d")
         if self.profile is not None:
             e1.record()
             hin, win = x.H, x.W

@@ -35,7 +35,8 @@ class _Warp(torch.autograd.Function):
         (flo,) = ctx.saved_tensors
         B, C, H, W = grad_out.shape
         gx = torch.zeros_like(grad_out)
-        L.check(L.lib().rrv_warp_backward(grad_out.contiguous().data_ptr(), flo.data_ptr(), B, C, H, W, gx.data_ptr(),
+        grad_out = grad_out.contiguous()
+        L.check(L.lib().rrv_warp_backward(grad_out.data_ptr(), flo.data_ptr(), B, C, H, W, gx.data_ptr(),
                                           L.stream()), "rrv_warp_backward")
         return gx, None
 
@@ -53,7 +54,8 @@ def warp_indices(flo):
     dummy = torch.zeros((B, 1, H, W), dtype=torch.float32, device=flo.device)
     out = torch.empty_like(dummy)
     idx = torch.empty((B, H, W, 2), dtype=torch.int32, device=flo.device)
-    L.check(L.lib().rrv_warp_nearest_border(dummy.data_ptr(), flo.contiguous().data_ptr(), B, 1, H, W, out.data_ptr(),
+    flo = flo.contiguous()
+    L.check(L.lib().rrv_warp_nearest_border(dummy.data_ptr(), flo.data_ptr(), B, 1, H, W, out.data_ptr(),
                                             idx.data_ptr(), L.stream()), "rrv_warp_nearest_border")
     return idx
 
