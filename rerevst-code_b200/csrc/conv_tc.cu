@@ -20,9 +20,12 @@
 // to a 2x2 conv over the low-resolution input with summed weights (9 -> 4 taps); the four phases
 // are four GEMMs over the same low-res tile that scatter to interleaved output pixels.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) and TMEM owner,
-// warps 2..5 = epilogue (tcgen05.ld -> fused pointwise chain -> 16-byte stores).
+// warps 2..9 = epilogue (tcgen05.ld -> fused pointwise chain -> 16-byte stores); the per-channel
+// constants of the chain are gathered once per CTA into a shared-memory table.
 #include <cuda.h>
+#include <math_constants.h>
 
+#include <cstring>
 #include <mutex>
 
 #include "rrv_common.cuh"
@@ -36,17 +39,31 @@ constexpr int BM = 128;          // output pixels per tile (= TMEM lanes)
 constexpr int BK = 64;           // channels per k-step (128-byte rows)
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int MAX_STAGES = 8;
-constexpr int TC_THREADS = 192;
+constexpr int EPI_WARPS = 8;      // two per TMEM lane quadrant, alternating 32-column chunks
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int TAB_BYTES = 48;     // per-channel epilogue constants: 11 floats (+1 pad)
 constexpr int SMEM_LIMIT = 227 * 1024 - 1024;   // dynamic part: the opt-in maximum minus the static barriers
 
 struct TcTune {
     int max_bn = 256;
-    int tile_w = 16;
-    int max_stages = 6;
+    int tile_w = 16;        // v1 only
+    int max_stages = 6;     // v1 only
+    int version = 2;        // main loop: 1 = one box per tap, 2 = row-reuse / shared weight tiles
+    int mt = 2;             // v2: M tiles (128 pixels each) per weight tile
+    int max_bn_ups = 64;    // v2: Cout tile of the nearest-x2 convolutions (4 MT accumulators)
+    int ups_v1 = 1;         // nearest-x2 convolutions use the v1 main loop
 };
 TcTune g_tune;
 
+struct OutDesc {
+    int H, W, Cout, out_mode, out_C;
+    uint16_t* out_hi;
+    uint16_t* out_lo;
+    float* out_f32;
+};
+
 struct TcParams {
+    OutDesc o;
     int N, H, W;            // output
     int in_H, in_W;         // input (H/2, W/2 when ups)
     int Cout, Cout_pad;
@@ -60,10 +77,6 @@ struct TcParams {
     int stages;
     int x3;
     int acc_stride, tmem_cols;
-    int out_mode, out_C;
-    uint16_t* out_hi;
-    uint16_t* out_lo;
-    float* out_f32;
     EpiDev ep;
 };
 
@@ -99,10 +112,57 @@ __device__ __forceinline__ void tap_offset(const TcParams& p, const TileCoord& c
     }
 }
 
-__device__ __forceinline__ void store_group(const TcParams& p, const float* v, int n, int oy, int ox, int c0, int nvalid) {
+// Shared-memory table of the per-channel constants of the fused pointwise chain, one array of
+// Cout_pad floats per constant (absent stages get their identity values).
+enum { T_BIAS = 0, T_M1, T_R1, T_LO1, T_HI1, T_M2, T_R2, T_LO2, T_HI2, T_SCALE, T_SHIFT, T_COUNT };
+enum { EPI_N1 = 1, EPI_RES = 2, EPI_N2 = 4, EPI_AFF = 8 };
+
+__device__ __forceinline__ void fill_epilogue_table(float* s_tab, const EpiDev& e, int Cout, int Cout_pad, int nthreads) {
+    for (int ch = threadIdx.x; ch < Cout_pad; ch += nthreads) {
+        const bool in = ch < Cout;
+        const int C = Cout;
+        s_tab[T_BIAS * Cout_pad + ch] = (in && e.bias) ? e.bias[ch] : 0.0f;
+        s_tab[T_M1 * Cout_pad + ch] = (in && e.norm1) ? e.norm1[ch] : 0.0f;
+        s_tab[T_R1 * Cout_pad + ch] = (in && e.norm1) ? e.norm1[C + ch] : 1.0f;
+        s_tab[T_LO1 * Cout_pad + ch] = (in && e.norm1) ? e.norm1[2 * C + ch] : -CUDART_INF_F;
+        s_tab[T_HI1 * Cout_pad + ch] = (in && e.norm1) ? e.norm1[3 * C + ch] : CUDART_INF_F;
+        s_tab[T_M2 * Cout_pad + ch] = (in && e.norm2) ? e.norm2[ch] : 0.0f;
+        s_tab[T_R2 * Cout_pad + ch] = (in && e.norm2) ? e.norm2[C + ch] : 1.0f;
+        s_tab[T_LO2 * Cout_pad + ch] = (in && e.norm2) ? e.norm2[2 * C + ch] : -CUDART_INF_F;
+        s_tab[T_HI2 * Cout_pad + ch] = (in && e.norm2) ? e.norm2[3 * C + ch] : CUDART_INF_F;
+        s_tab[T_SCALE * Cout_pad + ch] = (in && e.affine) ? e.affine[ch] : 1.0f;
+        s_tab[T_SHIFT * Cout_pad + ch] = (in && e.affine) ? e.affine[C + ch] : 0.0f;
+    }
+}
+
+__device__ __forceinline__ void lds8(const float* p, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// 8 fp32 values -> 8 bf16 hi + 8 bf16 lo (= bf16(v - hi)), two values per conversion instruction.
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+        const float r0 = v[2 * i] - __uint_as_float(hw[i] << 16);
+        const float r1 = v[2 * i + 1] - __uint_as_float(hw[i] & 0xffff0000u);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+        lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    hi = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    lo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
+__device__ __forceinline__ void store_group(const OutDesc& p, const float* v, int n, int oy, int ox, int c0, int nvalid) {
     const long long pix = ((long long)n * p.H + oy) * p.W + ox;
     if (p.out_mode == RRV_OUT_PLANES) {
-        store8(p.out_hi + pix * p.Cout + c0, p.out_lo ? p.out_lo + pix * p.Cout + c0 : nullptr, 0, v);
+        uint4 hi, lo;
+        split8(v, hi, lo);
+        *reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + c0) = hi;
+        if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + c0) = lo;
     } else if (p.out_mode == RRV_OUT_F32_NHWC) {
         float* o = p.out_f32 + pix * p.Cout + c0;
         if (nvalid == 8) {
@@ -121,6 +181,106 @@ __device__ __forceinline__ void store_group(const TcParams& p, const float* v, i
     }
 }
 
+// One 32-channel chunk of one accumulator row (= one output pixel) through the fused pointwise
+// chain: bias -> act -> saved-stat norm -> + residual -> saved-stat norm -> AdaIN -> store.
+// cb = first global output channel of the chunk, col0 = its first column inside the Cout tile.
+// FLAGS >= 0 fixes the set of stages at compile time (EPI_* bits); FLAGS < 0 reads it from `e`.
+template <int FLAGS>
+__device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e, const float* s_tab, int ts, uint32_t taddr,
+                                               bool valid, int n, int oy, int ox, int cb, int col0, int BN) {
+    const bool has_n1 = FLAGS >= 0 ? (FLAGS & EPI_N1) != 0 : e.norm1 != nullptr;
+    const bool has_res = FLAGS >= 0 ? (FLAGS & EPI_RES) != 0 : e.res_hi != nullptr;
+    const bool has_n2 = FLAGS >= 0 ? (FLAGS & EPI_N2) != 0 : e.norm2 != nullptr;
+    const bool has_aff = FLAGS >= 0 ? (FLAGS & EPI_AFF) != 0 : e.affine != nullptr;
+    const bool res_x3 = e.res_lo != nullptr;
+    uint32_t r[32];
+    ptx::tmem_ld32_issue(taddr, r);
+    // the residual of the whole chunk goes in flight while the TMEM load completes
+    uint4 rh[4], rl[4];
+    const bool full32 = cb + 32 <= o.Cout && col0 + 32 <= BN;
+    long long res_off = 0;
+    if (has_res) {
+        res_off = (long long)n * e.res_batch_stride + ((long long)(oy >> e.res_shift) * e.res_W + (ox >> e.res_shift)) * e.C;
+        if (valid && full32) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                rh[g] = *reinterpret_cast<const uint4*>(e.res_hi + res_off + cb + g * 8);
+                if (res_x3) rl[g] = *reinterpret_cast<const uint4*>(e.res_lo + res_off + cb + g * 8);
+            }
+        }
+    }
+    ptx::tmem_ld32_wait(r);
+    if (!valid) return;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const int c0 = cb + g * 8;
+        if (c0 >= o.Cout || col0 + g * 8 >= BN) continue;
+        float x[8], k0[8], k1[8];
+        lds8(s_tab + T_BIAS * ts + c0, k0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(r[g * 8 + i]) + k0[i];
+        if (e.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.0f);
+        } else if (e.act == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = x[i] > 0.0f ? x[i] : 0.2f * x[i];
+        }
+        if (has_n1) {
+            lds8(s_tab + T_M1 * ts + c0, k0);
+            lds8(s_tab + T_R1 * ts + c0, k1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = (x[i] - k0[i]) * k1[i];
+            lds8(s_tab + T_LO1 * ts + c0, k0);
+            lds8(s_tab + T_HI1 * ts + c0, k1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = fminf(k1[i], fmaxf(k0[i], x[i]));
+        }
+        if (has_res) {
+            if (full32) {
+                const uint32_t hw[4] = {rh[g].x, rh[g].y, rh[g].z, rh[g].w};
+                const uint32_t lw[4] = {rl[g].x, rl[g].y, rl[g].z, rl[g].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float a = __uint_as_float(hw[i] << 16), b = __uint_as_float(hw[i] & 0xffff0000u);
+                    if (res_x3) {
+                        a += __uint_as_float(lw[i] << 16);
+                        b += __uint_as_float(lw[i] & 0xffff0000u);
+                    }
+                    x[2 * i] += a;
+                    x[2 * i + 1] += b;
+                }
+            } else {                              // ragged channel tail (never on the per-frame path)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int cc = c0 + i;
+                    float rr = cc < o.Cout ? bf16_to_f32(e.res_hi[res_off + cc]) : 0.0f;
+                    if (res_x3 && cc < o.Cout) rr += bf16_to_f32(e.res_lo[res_off + cc]);
+                    x[i] += rr;
+                }
+            }
+        }
+        if (has_n2) {
+            lds8(s_tab + T_M2 * ts + c0, k0);
+            lds8(s_tab + T_R2 * ts + c0, k1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = (x[i] - k0[i]) * k1[i];
+            lds8(s_tab + T_LO2 * ts + c0, k0);
+            lds8(s_tab + T_HI2 * ts + c0, k1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = fminf(k1[i], fmaxf(k0[i], x[i]));
+        }
+        if (has_aff) {
+            lds8(s_tab + T_SCALE * ts + c0, k0);
+            lds8(s_tab + T_SHIFT * ts + c0, k1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = x[i] * k0[i] + k1[i];
+        }
+        store_group(o, x, n, oy, ox, c0, c0 + 8 <= o.Cout ? 8 : o.Cout - c0);
+    }
+}
+
+template <int FLAGS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -145,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(ptx::smem_u32(&s_tfull[a]), 1);
-            ptx::mbar_init(ptx::smem_u32(&s_tempty[a]), 4);     // one arrival per epilogue warp
+            ptx::mbar_init(ptx::smem_u32(&s_tempty[a]), EPI_WARPS);     // one arrival per epilogue warp
         }
         ptx::fence_barrier_init();
     }
@@ -157,6 +317,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             ptx::prefetch_tmap(&map_b_lo);
         }
     }
+    float* s_tab = reinterpret_cast<float*>(smem_raw + (smem_base - ptx::smem_u32(smem_raw)) + (uint32_t)p.stages * stage_bytes);
+    fill_epilogue_table(s_tab, p.ep, p.Cout, p.Cout_pad, TC_THREADS);
     if (warp == 1) {
         ptx::tmem_alloc(ptx::smem_u32(&s_tmem_base), (uint32_t)p.tmem_cols);
         ptx::tmem_relinquish();
@@ -207,23 +369,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             for (int ks = 0; ks < ksteps; ++ks) {
                 ptx::mbar_wait(ptx::smem_u32(&s_full[stage]), phase);
                 ptx::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sb = smem_base + (uint32_t)stage * stage_bytes;
-                    const uint64_t a_hi = ptx::make_smem_desc_sw128(sb);
-                    const uint64_t b_hi = ptx::make_smem_desc_sw128(sb + off_b_hi);
-                    const uint64_t a_lo = ptx::make_smem_desc_sw128(sb + off_a_lo);
-                    const uint64_t b_lo = ptx::make_smem_desc_sw128(sb + off_b_lo);
-#pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t adv = (uint64_t)(k * 2);       // 16 bf16 = 32 bytes = 2 x 16-byte units
-                        ptx::mma_bf16(d_tmem, a_hi + adv, b_hi + adv, idesc, (ks | k) != 0);
-                        if (p.x3) {
-                            ptx::mma_bf16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
-                            ptx::mma_bf16(d_tmem, a_lo + adv, b_hi + adv, idesc, 1u);
-                        }
-                    }
-                    ptx::mma_commit(ptx::smem_u32(&s_empty[stage]));          // frees the smem slot when the MMAs retire
-                    if (ks == ksteps - 1) ptx::mma_commit(ptx::smem_u32(&s_tfull[as]));
+                const uint32_t sb = smem_base + (uint32_t)stage * stage_bytes;
+                const uint32_t empty_bar = ptx::smem_u32(&s_empty[stage]), tfull_bar = ptx::smem_u32(&s_tfull[as]);
+                if (ptx::elect_one()) {
+                    ptx::mma_kblock(d_tmem, sb, sb + off_a_lo, sb + off_b_hi, sb + off_b_lo, idesc, p.x3 != 0, ks == 0);
+                    ptx::mma_commit(empty_bar);                               // frees the smem slot when the MMAs retire
+                    if (ks == ksteps - 1) ptx::mma_commit(tfull_bar);
                 }
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -231,11 +382,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             if (++as == 2) { as = 0; aphase ^= 1u; }
         }
     } else {
-        // ================= epilogue (warps 2..5; TMEM lane quadrant = warp % 4) =================
+        // ================= epilogue (warps 2..9; TMEM lane quadrant = warp % 4) =================
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;                 // which 32-column chunks this warp takes
         const int m = quad * 32 + lane;
         const int ty = m >> p.tw_shift, tx = m & ((1 << p.tw_shift) - 1);
         const int nchunks = (p.BN + 31) / 32;
+        const EpiDev& e = p.ep;
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -247,31 +400,249 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             ptx::mbar_wait(ptx::smem_u32(&s_tfull[as]), aphase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(as * p.acc_stride) + ((uint32_t)(quad * 32) << 16);
-            for (int ch = 0; ch < nchunks; ++ch) {
-                float v[32];
-                ptx::tmem_ld32(taddr + (uint32_t)(ch * 32), v);
-                if (valid) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int c0 = c.n0 + ch * 32 + g * 8;
-                        if (c0 >= p.Cout || ch * 32 + g * 8 >= p.BN) continue;
-                        if (c0 + 8 <= p.Cout) {
-                            apply_epilogue<8>(p.ep, v + g * 8, c.n, oy, ox, c0);
-                            store_group(p, v + g * 8, c.n, oy, ox, c0, 8);
-                        } else {
-                            const int nv = p.Cout - c0;
-#pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                if (k < nv) apply_epilogue<1>(p.ep, v + g * 8 + k, c.n, oy, ox, c0 + k);
-                            store_group(p, v + g * 8, c.n, oy, ox, c0, nv);
-                        }
-                    }
-                }
-            }
+            for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4)
+                epilogue_chunk<FLAGS>(p.o, e, s_tab, p.Cout_pad, taddr + (uint32_t)(ch * 32), valid, c.n, oy, ox, c.n0 + ch * 32, ch * 32, p.BN);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&s_tempty[as]));
             if (++as == 2) { as = 0; aphase ^= 1u; }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    }
+}
+
+// =====================================================================================================
+// v2 main loop: fewer bytes through the L2 -> SM crossbar per MMA cycle (v1 is bound by it: ncu shows
+// ~10.9 TB/s of xbar2l1tex traffic and the tensor pipe at 50% on the 256-channel layers).
+//   * spatial tile = 16 rows x 8 columns per 128-row M tile, MT M tiles stacked vertically;
+//   * ONE A box per (64-channel chunk, dx): (16 MT + 2) rows x 8 columns.  The three dy taps read
+//     it at row offsets dy * 8 rows = dy * 1024 bytes, i.e. whole 128-byte-swizzle atoms, so the
+//     operand descriptor only moves its start address: 3 loads instead of 9 per chunk;
+//   * every weight tile (tap x chunk) is used by all MT M tiles before its slot is released
+//     (B bytes per MMA halve with MT = 2), or stays resident for the whole kernel when all taps
+//     fit (the 64 -> 64 full-resolution layers);
+//   * the four phases of a nearest-x2 convolution share the three A boxes (16 -> 3 loads per chunk)
+//     and accumulate into 4 MT separate TMEM accumulators.
+// A and B travel through separate rings (A: a_stages, B: b_slots) filled by one producer thread in
+// consumption order.
+constexpr int MAX_B_SLOTS = 16;
+constexpr int MAX_GRP = 8;
+
+struct Grp {                // one weight tile consumed against the current A box
+    int btile;              // index into the [tap][Cout_pad][Cin] blob
+    int acc;                // accumulator of M tile 0 (M tile mt uses acc + mt)
+    int arow;               // row offset (in 8-pixel rows) of the A operand inside the box
+    int first;              // first contribution to this accumulator at chunk 0: overwrite
+};
+
+struct Tc2Params {
+    OutDesc o;
+    int N, in_H, in_W;
+    int Cout, Cout_pad, kchunks;
+    int ups;                // 1: four output phases per input pixel
+    int MT, halo;
+    int nA;                 // A boxes per chunk (3, or 1 for 1x1)
+    int a_dx[3];
+    int ngrp[3];
+    Grp grp[3][MAX_GRP];
+    int nacc;               // accumulators per tile set = (ups ? 4 : 1) * MT
+    int tiles_x, tiles_y, n_ntiles, total_tiles;
+    int BN, x3;
+    int a_stages, b_slots, b_resident;
+    int a_plane_bytes;      // (16 MT + 2 halo) * 1024
+    int acc_stride, set_stride, bufs, tmem_cols;
+    EpiDev ep;
+};
+
+template <int FLAGS>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const Tc2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t s_afull[MAX_STAGES], s_aempty[MAX_STAGES], s_bfull[MAX_B_SLOTS], s_bempty[MAX_B_SLOTS],
+        s_tfull[2], s_tempty[2];
+    __shared__ uint32_t s_tmem_base;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t planes = p.x3 ? 2u : 1u;
+    const uint32_t a_stage_bytes = planes * (uint32_t)p.a_plane_bytes;
+    const uint32_t b_plane_bytes = (uint32_t)p.BN * 128u;
+    const uint32_t b_slot_bytes = planes * b_plane_bytes;
+    const uint32_t b_base = smem_base + (uint32_t)p.a_stages * a_stage_bytes;
+    const uint32_t tab_off = (uint32_t)p.a_stages * a_stage_bytes + (uint32_t)p.b_slots * b_slot_bytes;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.a_stages; ++s) {
+            ptx::mbar_init(ptx::smem_u32(&s_afull[s]), 1);
+            ptx::mbar_init(ptx::smem_u32(&s_aempty[s]), 1);
+        }
+        for (int s = 0; s < p.b_slots; ++s) {
+            ptx::mbar_init(ptx::smem_u32(&s_bfull[s]), 1);
+            ptx::mbar_init(ptx::smem_u32(&s_bempty[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(ptx::smem_u32(&s_tfull[a]), 1);
+            ptx::mbar_init(ptx::smem_u32(&s_tempty[a]), EPI_WARPS);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&map_a_hi);
+        ptx::prefetch_tmap(&map_b_hi);
+        if (p.x3) {
+            ptx::prefetch_tmap(&map_a_lo);
+            ptx::prefetch_tmap(&map_b_lo);
+        }
+    }
+    float* s_tab = reinterpret_cast<float*>(smem_raw + (smem_base - ptx::smem_u32(smem_raw)) + tab_off);
+    fill_epilogue_table(s_tab, p.ep, p.Cout, p.Cout_pad, TC_THREADS);
+    if (warp == 1) {
+        ptx::tmem_alloc(ptx::smem_u32(&s_tmem_base), (uint32_t)p.tmem_cols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = s_tmem_base;
+    const int rows_per_set = 16 * p.MT;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            bool first_set = true;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int n0 = (t % p.n_ntiles) * p.BN; t /= p.n_ntiles;
+                const int x0 = (t % p.tiles_x) * 8; t /= p.tiles_x;
+                const int y0 = (t % p.tiles_y) * rows_per_set;
+                const int n = t / p.tiles_y;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    for (int j = 0; j < p.nA; ++j) {
+                        ptx::mbar_wait(ptx::smem_u32(&s_aempty[sa]), pa ^ 1u);
+                        const uint32_t full = ptx::smem_u32(&s_afull[sa]);
+                        const uint32_t dst = smem_base + (uint32_t)sa * a_stage_bytes;
+                        ptx::mbar_expect_tx(full, a_stage_bytes);
+                        ptx::tma_load_4d(dst, &map_a_hi, full, kc * BK, x0 + p.a_dx[j], y0 - p.halo, n);
+                        if (p.x3) ptx::tma_load_4d(dst + (uint32_t)p.a_plane_bytes, &map_a_lo, full, kc * BK, x0 + p.a_dx[j], y0 - p.halo, n);
+                        if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+                        for (int g = 0; g < p.ngrp[j]; ++g) {
+                            const int btile = p.grp[j][g].btile;
+                            int slot;
+                            if (p.b_resident) {
+                                if (!first_set) continue;
+                                slot = btile * p.kchunks + kc;
+                            } else {
+                                slot = sb;
+                                ptx::mbar_wait(ptx::smem_u32(&s_bempty[sb]), pb ^ 1u);
+                                if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
+                            }
+                            const uint32_t bfull = ptx::smem_u32(&s_bfull[slot]);
+                            const uint32_t bdst = b_base + (uint32_t)slot * b_slot_bytes;
+                            ptx::mbar_expect_tx(bfull, b_slot_bytes);
+                            ptx::tma_load_2d(bdst, &map_b_hi, bfull, kc * BK, btile * p.Cout_pad + n0);
+                            if (p.x3) ptx::tma_load_2d(bdst + b_plane_bytes, &map_b_lo, bfull, kc * BK, btile * p.Cout_pad + n0);
+                        }
+                    }
+                }
+                first_set = false;
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = ptx::make_idesc_bf16(BM, p.BN);
+        int sa = 0, sb = 0, as = 0;
+        uint32_t pa = 0, pb = 0, aphase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            ptx::mbar_wait(ptx::smem_u32(&s_tempty[as]), aphase ^ 1u);
+            ptx::tc_fence_after();
+            const uint32_t d_set = tmem_base + (uint32_t)(as * p.set_stride);
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                for (int j = 0; j < p.nA; ++j) {
+                    ptx::mbar_wait(ptx::smem_u32(&s_afull[sa]), pa);
+                    const uint32_t a_base = smem_base + (uint32_t)sa * a_stage_bytes;
+                    for (int g = 0; g < p.ngrp[j]; ++g) {
+                        const Grp gr = p.grp[j][g];
+                        int slot;
+                        if (p.b_resident) {
+                            slot = gr.btile * p.kchunks + kc;
+                            ptx::mbar_wait(ptx::smem_u32(&s_bfull[slot]), 0u);
+                        } else {
+                            slot = sb;
+                            ptx::mbar_wait(ptx::smem_u32(&s_bfull[sb]), pb);
+                        }
+                        ptx::tc_fence_after();
+                        const uint32_t bs = b_base + (uint32_t)slot * b_slot_bytes;
+                        const bool overwrite = kc == 0 && gr.first != 0;
+                        const uint32_t a0 = a_base + (uint32_t)(gr.arow * 1024);
+                        const uint32_t d0 = d_set + (uint32_t)(gr.acc * p.acc_stride);
+                        const uint32_t bempty_bar = ptx::smem_u32(&s_bempty[sb]);
+                        if (ptx::elect_one()) {
+                            ptx::mma_kblock(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
+                            if (p.MT == 2)
+                                ptx::mma_kblock(d0 + (uint32_t)p.acc_stride, a0 + 16384u, a0 + 16384u + (uint32_t)p.a_plane_bytes, bs,
+                                                bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
+                            if (!p.b_resident) ptx::mma_commit(bempty_bar);
+                        }
+                        __syncwarp();
+                        if (!p.b_resident) {
+                            if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
+                        }
+                    }
+                    const uint32_t aempty_bar = ptx::smem_u32(&s_aempty[sa]), tfull_bar = ptx::smem_u32(&s_tfull[as]);
+                    if (ptx::elect_one()) {
+                        ptx::mma_commit(aempty_bar);
+                        if (kc == p.kchunks - 1 && j == p.nA - 1) ptx::mma_commit(tfull_bar);
+                    }
+                    __syncwarp();
+                    if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+                }
+            }
+            if (++as == p.bufs) { as = 0; aphase ^= 1u; }
+        }
+    } else {
+        // ================= epilogue (warps 2..9; TMEM lane quadrant = warp % 4) =================
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int m = quad * 32 + lane;
+        const int ty = m >> 3, tx = m & 7;
+        const int nchunks = (p.BN + 31) / 32;
+        const EpiDev& e = p.ep;
+        int as = 0;
+        uint32_t aphase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            int t = tile;
+            const int n0 = (t % p.n_ntiles) * p.BN; t /= p.n_ntiles;
+            const int x0 = (t % p.tiles_x) * 8; t /= p.tiles_x;
+            const int y0 = (t % p.tiles_y) * rows_per_set;
+            const int n = t / p.tiles_y;
+            ptx::mbar_wait(ptx::smem_u32(&s_tfull[as]), aphase);
+            ptx::tc_fence_after();
+            const uint32_t t_set = tmem_base + (uint32_t)(as * p.set_stride) + ((uint32_t)(quad * 32) << 16);
+            const int units = p.nacc * nchunks;            // (accumulator, 32-column chunk) pairs
+            for (int u = half; u < units; u += EPI_WARPS / 4) {
+                const int acc = u / nchunks, ch = u - acc * nchunks;
+                const int phase = acc / p.MT, mt = acc - phase * p.MT;
+                const int iy = y0 + 16 * mt + ty, ix = x0 + tx;
+                const bool valid = iy < p.in_H && ix < p.in_W;
+                const int oy = p.ups ? 2 * iy + (phase >> 1) : iy;
+                const int ox = p.ups ? 2 * ix + (phase & 1) : ix;
+                epilogue_chunk<FLAGS>(p.o, e, s_tab, p.Cout_pad, t_set + (uint32_t)(acc * p.acc_stride + ch * 32), valid, n, oy, ox,
+                                      n0 + ch * 32, ch * 32, p.BN);
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&s_tempty[as]));
+            if (++as == p.bufs) { as = 0; aphase ^= 1u; }
         }
     }
 
@@ -369,6 +740,13 @@ int encode_w_map(CUtensorMap* m, const void* base, int rows, int Cin, int BN) {
 
 int cout_pad_of(int Cout) { return (Cout + 15) / 16 * 16; }
 
+OutDesc make_out(const rrv_conv* p) {
+    OutDesc o;
+    o.H = p->H; o.W = p->W; o.Cout = p->Cout; o.out_mode = p->out_mode; o.out_C = p->out_C;
+    o.out_hi = (uint16_t*)p->out_hi; o.out_lo = (uint16_t*)p->out_lo; o.out_f32 = p->out_f32;
+    return o;
+}
+
 int pick_bn(int Cout_pad) {
     int bn = std::min(Cout_pad, g_tune.max_bn);
     while (bn > 16 && Cout_pad % bn != 0) bn -= 16;
@@ -386,6 +764,174 @@ int num_sms() {
     return n;
 }
 
+
+int epi_flags(const rrv_epilogue& e) {
+    return (e.norm1 ? EPI_N1 : 0) | (e.res_hi ? EPI_RES : 0) | (e.norm2 ? EPI_N2 : 0) | (e.affine ? EPI_AFF : 0);
+}
+
+template <int FLAGS>
+int launch_tc1(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
+               const CUtensorMap& mb_lo, const TcParams& d) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        RRV_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    conv_tc_kernel<FLAGS><<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, d);
+    return check_launch("conv_tc_kernel");
+}
+
+template <int FLAGS>
+int launch_tc2(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
+               const CUtensorMap& mb_lo, const Tc2Params& d) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        RRV_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(conv_tc2_kernel): %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    conv_tc2_kernel<FLAGS><<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, d);
+    return check_launch("conv_tc2_kernel");
+}
+
+int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
+    const int ups = p->ups ? 1 : 0;
+    Tc2Params d;
+    memset(&d, 0, sizeof(d));
+    d.o = make_out(p);
+    d.N = p->N;
+    d.in_H = p->H >> ups; d.in_W = p->W >> ups;
+    d.Cout = p->Cout;
+    d.Cout_pad = cout_pad_of(p->Cout);
+    d.kchunks = p->Cin / BK;
+    d.ups = ups;
+    d.x3 = p->in_lo != nullptr;
+    d.halo = (p->ksize == 3) ? 1 : 0;
+    const int planes = d.x3 ? 2 : 1;
+    const int nph = ups ? 4 : 1;
+    const int btiles = ups ? 16 : p->ksize * p->ksize;
+
+    // ---- tile shape: Cout tile BN, M tiles per weight tile MT ----
+    int max_bn = ups ? std::min(g_tune.max_bn_ups, g_tune.max_bn) : g_tune.max_bn;
+    int BN = std::min(d.Cout_pad, max_bn);
+    while (BN > 16 && d.Cout_pad % BN != 0) BN -= 16;
+    int MT = std::max(1, std::min(g_tune.mt, 2));
+    if (d.in_H <= 16) MT = 1;
+    const int budget = SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES;
+    int a_stage = 0, b_slot = 0;
+    // all weight tiles resident beats sharing them between two M tiles: prefer MT = 1 if that is what fits
+    if (MT == 2 && BN == d.Cout_pad && btiles * d.kchunks <= MAX_B_SLOTS) {
+        const int b_all = btiles * d.kchunks * planes * BN * 128;
+        const int a2 = planes * (32 + 2 * d.halo) * 1024, a1 = planes * (16 + 2 * d.halo) * 1024;
+        if (b_all + 2 * a2 > budget && b_all + 2 * a1 <= budget) MT = 1;
+    }
+    for (;;) {
+        const int acc_stride = (BN + 31) / 32 * 32;
+        a_stage = planes * (16 * MT + 2 * d.halo) * 1024;
+        b_slot = planes * BN * 128;
+        const bool tmem_ok = nph * MT * acc_stride <= 512;
+        const bool smem_ok = 2 * a_stage + 2 * b_slot <= budget;
+        if (tmem_ok && smem_ok) break;
+        if (MT > 1) { MT = 1; continue; }
+        RRV_REQUIRE(BN > 16, "rrv_conv2d(tcgen05 v2): no tile shape fits (Cout=%d)", p->Cout);
+        BN -= 16;
+        while (BN > 16 && d.Cout_pad % BN != 0) BN -= 16;
+    }
+    d.BN = BN; d.MT = MT;
+    d.n_ntiles = d.Cout_pad / BN;
+    d.acc_stride = (BN + 31) / 32 * 32;
+    d.nacc = nph * MT;
+    d.set_stride = d.nacc * d.acc_stride;
+    d.bufs = 2 * d.set_stride <= 512 ? 2 : 1;
+    d.tmem_cols = 32;
+    while (d.tmem_cols < d.bufs * d.set_stride) d.tmem_cols *= 2;
+    d.a_plane_bytes = (16 * MT + 2 * d.halo) * 1024;
+
+    // ---- rings ----
+    const int b_all = btiles * d.kchunks;
+    if (d.n_ntiles == 1 && b_all <= MAX_B_SLOTS && b_all * b_slot + 2 * a_stage <= budget) {
+        d.b_resident = 1;
+        d.b_slots = b_all;
+        d.a_stages = std::min(4, (budget - b_all * b_slot) / a_stage);
+    } else {
+        d.b_resident = 0;
+        d.a_stages = 2; d.b_slots = 2;
+        int rem = budget - 2 * a_stage - 2 * b_slot;
+        for (;;) {
+            if (d.b_slots < 4 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
+            if (d.a_stages < 3 && rem >= a_stage) { ++d.a_stages; rem -= a_stage; continue; }
+            if (d.b_slots < 8 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
+            break;
+        }
+    }
+
+    // ---- which weight tiles meet which A box ----
+    if (p->ksize == 1) {
+        d.nA = 1; d.a_dx[0] = 0; d.ngrp[0] = 1;
+        d.grp[0][0] = Grp{0, 0, 0, 1};
+    } else if (!ups) {
+        d.nA = 3;
+        for (int j = 0; j < 3; ++j) {
+            d.a_dx[j] = j - 1; d.ngrp[j] = 3;
+            for (int dy = 0; dy < 3; ++dy) d.grp[j][dy] = Grp{dy * 3 + j, 0, dy, (j == 0 && dy == 0) ? 1 : 0};
+        }
+    } else {
+        d.nA = 3;
+        bool seen[4] = {false, false, false, false};
+        for (int j = 0; j < 3; ++j) {
+            const int ox = j - 1;
+            d.a_dx[j] = ox;
+            int g = 0;
+            for (int py = 0; py < 2; ++py)
+                for (int a = 0; a < 2; ++a)
+                    for (int px = 0; px < 2; ++px) {
+                        const int b = ox - (px - 1);
+                        if (b < 0 || b > 1) continue;
+                        const int ph = py * 2 + px;
+                        d.grp[j][g++] = Grp{ph * 4 + a * 2 + b, ph * MT, py - 1 + a + 1, seen[ph] ? 0 : 1};
+                        seen[ph] = true;
+                    }
+            d.ngrp[j] = g;
+        }
+    }
+
+    d.tiles_x = ceil_div(d.in_W, 8);
+    d.tiles_y = ceil_div(d.in_H, 16 * MT);
+    const long long total = (long long)d.N * d.tiles_y * d.tiles_x * d.n_ntiles;
+    RRV_REQUIRE(total < (1LL << 31), "rrv_conv2d: too many tiles");
+    d.total_tiles = (int)total;
+    d.ep = make_epi(p->ep, p->Cout);
+    d.ep.lo_fp16 = 0;
+
+    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
+    const int rows = btiles * d.Cout_pad;
+    const uint16_t* w_hi = (const uint16_t*)p->w_tc;
+    const uint16_t* w_lo = w_hi + (long long)rows * p->Cin;
+    const int box_rows = 16 * MT + 2 * d.halo;
+    if (encode_act_map(&ma_hi, p->in_hi, d.N, d.in_H, d.in_W, p->Cin, 8, box_rows)) return 1;
+    if (encode_w_map(&mb_hi, w_hi, rows, p->Cin, BN)) return 1;
+    if (d.x3) {
+        if (encode_act_map(&ma_lo, p->in_lo, d.N, d.in_H, d.in_W, p->Cin, 8, box_rows)) return 1;
+        if (encode_w_map(&mb_lo, w_lo, rows, p->Cin, BN)) return 1;
+    } else {
+        ma_lo = ma_hi;
+        mb_lo = mb_hi;
+    }
+    const int smem = d.a_stages * a_stage + d.b_slots * b_slot + d.Cout_pad * TAB_BYTES + 1024;
+    const int flags = epi_flags(p->ep);
+    const int grid = std::min(d.total_tiles, num_sms());
+    switch (flags) {
+        case 0: return launch_tc2<0>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        case EPI_N1: return launch_tc2<EPI_N1>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        case EPI_RES: return launch_tc2<EPI_RES>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        case EPI_RES | EPI_N2 | EPI_AFF: return launch_tc2<EPI_RES | EPI_N2 | EPI_AFF>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        case EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF:
+            return launch_tc2<EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        default: return launch_tc2<-1>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+    }
+}
+
 }  // namespace
 
 int tc_tune(int max_bn, int tile_w, int max_stages) {
@@ -395,6 +941,17 @@ int tc_tune(int max_bn, int tile_w, int max_stages) {
     g_tune.max_bn = max_bn;
     g_tune.tile_w = tile_w;
     g_tune.max_stages = max_stages;
+    return 0;
+}
+
+int tc_tune2(int version, int mt, int max_bn_ups) {
+    RRV_REQUIRE(version == 1 || version == 2, "rrv_tc_tune2: version must be 1 or 2");
+    RRV_REQUIRE(mt == 1 || mt == 2, "rrv_tc_tune2: mt must be 1 or 2");
+    RRV_REQUIRE(max_bn_ups >= 16 && max_bn_ups <= 128 && max_bn_ups % 16 == 0, "rrv_tc_tune2: max_bn_ups must be a multiple of 16 in [16, 128]");
+    g_tune.version = version;
+    g_tune.mt = mt;
+    g_tune.max_bn_ups = max_bn_ups;
+    g_tune.ups_v1 = max_bn_ups <= 64 ? 1 : 0;     // asking for a wider ups tile selects the v2 ups path
     return 0;
 }
 
@@ -438,6 +995,10 @@ int conv2d_tc(const rrv_conv* p, cudaStream_t st) {
         RRV_REQUIRE(p->out_mode != RRV_OUT_F32_NCHW || p->out_C > 0, "rrv_conv2d: out_C must be set for NCHW output");
     }
 
+    // nearest-x2 layers: per-phase tiles with the widest Cout tile (v1) beat the shared-box main loop,
+    // whose 4 MT accumulators cap the Cout tile at 64 (operand fetch cost per MMA ~ 64 + N/2 cycles)
+    if (g_tune.version == 2 && !(ups && g_tune.ups_v1)) return conv2d_tc2(p, st);
+
     TcParams d;
     d.N = p->N; d.H = p->H; d.W = p->W;
     d.in_H = p->H >> ups; d.in_W = p->W >> ups;
@@ -461,16 +1022,13 @@ int conv2d_tc(const rrv_conv* p, cudaStream_t st) {
     d.total_tiles = (int)total;
     d.x3 = p->in_lo != nullptr;
     const int stage_bytes = (d.x3 ? 2 : 1) * (A_BYTES + d.BN * 128);
-    d.stages = std::min(g_tune.max_stages, (SMEM_LIMIT - 2048) / stage_bytes);
+    const int tab_bytes = d.Cout_pad * TAB_BYTES;
+    d.stages = std::min(g_tune.max_stages, (SMEM_LIMIT - 1024 - tab_bytes) / stage_bytes);
     RRV_REQUIRE(d.stages >= 2, "rrv_conv2d(tcgen05): tile does not fit shared memory (BN=%d)", d.BN);
     d.acc_stride = (d.BN + 31) / 32 * 32;
     d.tmem_cols = 32;
     while (d.tmem_cols < 2 * d.acc_stride) d.tmem_cols *= 2;
-    d.out_mode = p->out_mode;
-    d.out_C = p->out_C;
-    d.out_hi = (uint16_t*)p->out_hi;
-    d.out_lo = (uint16_t*)p->out_lo;
-    d.out_f32 = p->out_f32;
+    d.o = make_out(p);
     d.ep = make_epi(p->ep, p->Cout);
     d.ep.lo_fp16 = 0;
 
@@ -488,16 +1046,13 @@ int conv2d_tc(const rrv_conv* p, cudaStream_t st) {
         mb_lo = mb_hi;
     }
 
-    const int smem = d.stages * stage_bytes + 1024;
-    static int smem_set = 0;
-    if (smem > smem_set) {
-        const cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        RRV_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(e));
-        smem_set = SMEM_LIMIT;
-    }
+    const int smem = d.stages * stage_bytes + tab_bytes + 1024;
     const int grid = std::min(d.total_tiles, num_sms());
-    conv_tc_kernel<<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, d);
-    return check_launch("conv_tc_kernel");
+    switch (epi_flags(p->ep)) {
+        case 0: return launch_tc1<0>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        case EPI_N1: return launch_tc1<EPI_N1>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        default: return launch_tc1<-1>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+    }
 }
 
 }  // namespace rrv

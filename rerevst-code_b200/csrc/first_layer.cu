@@ -6,7 +6,7 @@
 
 namespace rrv {
 
-constexpr int FL_TH = 4, FL_TW = 16;
+constexpr int FL_TH = 8, FL_TW = 32;
 
 struct FirstDev {
     const void* src;
@@ -46,9 +46,11 @@ __device__ __forceinline__ void normalised_rgb(const FirstDev& p, int n, int y, 
     }
 }
 
+// Tile = 8 rows x 32 columns; thread = 4 adjacent pixels x 16 output channels, so every weight
+// float4 read from shared memory feeds 16 FMAs and the kernel is FFMA- rather than LDS-bound.
 __global__ void __launch_bounds__(256) first_layer_kernel(const FirstDev p) {
     constexpr int PH = FL_TH + 2, PW = FL_TW + 2;
-    __shared__ float s_in[3][PH][PW + 1];
+    __shared__ float s_in[3][PH][PW + 2];
     __shared__ __align__(16) float s_w[27][64];
     __shared__ float s_b[64];
     const int tid = threadIdx.x;
@@ -72,42 +74,55 @@ __global__ void __launch_bounds__(256) first_layer_kernel(const FirstDev p) {
     }
     __syncthreads();
 
-    const int q = tid & 3, pix = tid >> 2;
-    const int r = pix / FL_TW, c = pix % FL_TW;
-    const int oy = oy0 + r, ox = ox0 + c;
-    float acc[16];
+    const int q = tid & 3, pg = tid >> 2;
+    const int r = pg >> 3, c0 = (pg & 7) * 4;
+    float acc[4][16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = s_b[q * 16 + k];
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) acc[j][k] = s_b[q * 16 + k];
 #pragma unroll
     for (int ch = 0; ch < 3; ++ch)
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
+        for (int dy = 0; dy < 3; ++dy) {
+            float a[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) a[i] = s_in[ch][r + dy][c0 + i];
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
-                const float a = s_in[ch][r + dy][c + dx];
                 const float4* wp = reinterpret_cast<const float4*>(&s_w[ch * 9 + dy * 3 + dx][q * 16]);
 #pragma unroll
                 for (int k4 = 0; k4 < 4; ++k4) {
                     const float4 w = wp[k4];
-                    acc[4 * k4 + 0] = fmaf(a, w.x, acc[4 * k4 + 0]);
-                    acc[4 * k4 + 1] = fmaf(a, w.y, acc[4 * k4 + 1]);
-                    acc[4 * k4 + 2] = fmaf(a, w.z, acc[4 * k4 + 2]);
-                    acc[4 * k4 + 3] = fmaf(a, w.w, acc[4 * k4 + 3]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[j][4 * k4 + 0] = fmaf(a[j + dx], w.x, acc[j][4 * k4 + 0]);
+                        acc[j][4 * k4 + 1] = fmaf(a[j + dx], w.y, acc[j][4 * k4 + 1]);
+                        acc[j][4 * k4 + 2] = fmaf(a[j + dx], w.z, acc[j][4 * k4 + 2]);
+                        acc[j][4 * k4 + 3] = fmaf(a[j + dx], w.w, acc[j][4 * k4 + 3]);
+                    }
                 }
             }
-    if (oy >= p.H || ox >= p.W) return;
+        }
+    const int oy = oy0 + r;
+    if (oy >= p.H) return;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = fmaxf(acc[k], 0.0f);
-    const long long o = (((long long)n * p.H + oy) * p.W + ox) * 64 + q * 16;
-    if (p.out_hi != nullptr) {
-        store8(p.out_hi + o, p.out_lo ? p.out_lo + o : nullptr, p.lo_fp16, acc);
-        store8(p.out_hi + o + 8, p.out_lo ? p.out_lo + o + 8 : nullptr, p.lo_fp16, acc + 8);
-    }
-    if (p.out_f32 != nullptr) {
+    for (int j = 0; j < 4; ++j) {
+        const int ox = ox0 + c0 + j;
+        if (ox >= p.W) continue;
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-            *reinterpret_cast<float4*>(p.out_f32 + o + 4 * k4) =
-                make_float4(acc[4 * k4], acc[4 * k4 + 1], acc[4 * k4 + 2], acc[4 * k4 + 3]);
+        for (int k = 0; k < 16; ++k) acc[j][k] = fmaxf(acc[j][k], 0.0f);
+        const long long o = (((long long)n * p.H + oy) * p.W + ox) * 64 + q * 16;
+        if (p.out_hi != nullptr) {
+            store8(p.out_hi + o, p.out_lo ? p.out_lo + o : nullptr, p.lo_fp16, acc[j]);
+            store8(p.out_hi + o + 8, p.out_lo ? p.out_lo + o + 8 : nullptr, p.lo_fp16, acc[j] + 8);
+        }
+        if (p.out_f32 != nullptr) {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)
+                *reinterpret_cast<float4*>(p.out_f32 + o + 4 * k4) =
+                    make_float4(acc[j][4 * k4], acc[j][4 * k4 + 1], acc[j][4 * k4 + 2], acc[j][4 * k4 + 3]);
+        }
     }
 }
 

@@ -112,6 +112,7 @@ class StyleEngine:
         self.filters = {}            # "Filter1" -> (wf1, wf2) fp32 [32,32]
         self.fw = {}                 # "Filter1" -> (ConvW down', ConvW up')
         self.samples = []
+        self.q1_sample = None        # Encoder output of the clip's first sampled frame when it lives on another rank (dist.py)
         self.stats_allgather = None  # set by dist.ShardedPrepass: part[5,C] -> parts[G,5,C]
         self._plans = {}
         self.profile = None          # list -> (label, start_event, end_event, flops) per conv launch (bench.py)
@@ -302,6 +303,7 @@ class StyleEngine:
     # ------------------------------------------------------------------ pre-pass
     def clean(self):
         self.samples = []
+        self.q1_sample = None
         self.stats = {}
         self.filters = {}
         self.fw = {}
@@ -315,6 +317,18 @@ class StyleEngine:
         else:
             N, H, W, _ = patch.shape
         self.samples.append(self._vgg("Encoder", patch.contiguous(), kind, True, N, H, W, "raw"))
+
+    @torch.no_grad()
+    def add_q1(self, patch, kind=0):
+        """Frame-parallel pre-pass: the clip's FIRST sampled frame, encoded on a rank that does not own
+        it.  Quirk Q1 (KernelFilter.compute, :223-230) filters only sample 0 and broadcasts its residual to
+        every sample, so every rank carries sample 0 through norm[0] -> Filter1..3; it does not enter this
+        rank's statistics."""
+        if kind == 0:
+            N, _, H, W = patch.shape
+        else:
+            N, H, W, _ = patch.shape
+        self.q1_sample = self._vgg("Encoder", patch.contiguous(), kind, True, N, H, W, "raw")
 
     def _fold_filter(self, f, wf1, wf2):
         """Fold the two predicted 32x32 matrices of a KernelFilter (apply_filter, :194-217) into its
@@ -360,13 +374,17 @@ class StyleEngine:
         tabs = self.style["tabs"]
         st["norm0"] = self._saved_stat(x)
         h = self._pointwise(x, make_epilogue(norm1=st["norm0"]))            # planes [N, h, w, 512]
+        # sample 0 of the CLIP (Q1): local sample 0 on the rank that owns it, q1_sample elsewhere
+        h0 = self._pointwise(self.q1_sample, make_epilogue(norm1=st["norm0"])) if self.q1_sample is not None else None
         del x
         for i, f in enumerate(FILTERS):
             wf1, wf2 = self._predict_filters(f, h)
             self._fold_filter(f, wf1, wf2)
             down, up = self.fw[f]
-            t = self._conv(down, h.slice0(), make_epilogue(bias=down.bias, act=2))
+            t = self._conv(down, h0 if h0 is not None else h.slice0(), make_epilogue(bias=down.bias, act=2))
             u0 = self._conv(up, t, make_epilogue(bias=up.bias), L.OUT_F32_NHWC)   # [1,h,w,512]
+            if h0 is not None and i < 2:
+                h0 = self._pointwise(u0, make_epilogue(res=h0))
             if i < 2:
                 h = self._pointwise(u0, make_epilogue(res=h), N=N, broadcast=True)
             else:
@@ -390,6 +408,7 @@ class StyleEngine:
             r = self._pointwise(r2, make_epilogue(norm1=st[block + ".norm2"], res=s, res_shift=1), to_f32=True)
             del r2
         self.samples = []
+        self.q1_sample = None
         self._plans = {}
 
     # ------------------------------------------------------------------ per-frame forward
