@@ -260,9 +260,29 @@ def main():
         clocks.start()
     ms_dev, launches = timed(lambda i: eng.forward(dev_frames[i % nfr], kind=1, out=out), args.steps, args.warmup)
     clk = clocks.stop() if rank == 0 else None
-    # ---- end-to-end arm: host uint8 in, host fp32 BGR out, every step ----
+    # ---- end-to-end arm: host uint8 in, host fp32 BGR out, every step (public API: Stylization.transfer_stream,
+    #      which overlaps the pinned H2D / D2H copies of neighbouring frames with the kernels) ----
     crop = (64, 64, h, w)
-    ms_e2e, _ = timed(lambda i: fw.transfer(host_frames[i % nfr], crop=crop), args.steps, args.warmup)
+
+    def e2e_run(steps):
+        n = 0
+        for res in fw.transfer_stream((host_frames[i % nfr] for i in range(steps)), crop=crop):
+            n += res.shape[0] > 0
+        return n
+
+    e2e_run(args.warmup)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(args.steps)
+    torch.cuda.synchronize()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    # synchronous variant (the reference's own call pattern: one blocking transfer() per frame)
+    ms_sync, _ = timed(lambda i: fw.transfer(host_frames[i % nfr], crop=crop), max(3, args.steps // 2), 1)
+    ms_sync /= max(3, args.steps // 2)
 
     # ---- per-launch breakdown of the convolution kernel (CUDA events around each launch) ----
     eng.profile = []
@@ -282,7 +302,14 @@ def main():
     fl = flops_per_frame(ph, pw)
     fps = world * args.steps / (ms_dev * 1e-3)
     fps_e2e = world * args.steps / (ms_e2e * 1e-3)
-    achieved = fl * (args.steps / (ms_dev * 1e-3)) / 1e12            # per GPU
+    frame_tflops = fl * (args.steps / (ms_dev * 1e-3)) / 1e12            # per GPU, whole frame
+    conv_alg = fl - 2.0 * 3 * 64 * 9 * ph * pw                            # conv1_1 runs in first_layer_kernel, not the TC kernel
+    conv_tflops = conv_alg / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and args.size == "1080p" and args.precision == "x3":
+        tj = json.load(open(tpath))
+        traffic = tj["conv_dram_bytes_per_frame"] / tj["conv_launches_per_frame"]
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -292,16 +319,20 @@ def main():
                                f"global mode, random-init weights, B=1 per step, {args.samples} pre-pass samples",
                    "frame": [h, w], "padded": [ph, pw], "precision": args.precision,
                    "kernels": {0: "ffma", 1: "tcgen05"}[eng.impl],
-                   "l2": "per-step working set ~10 GB of activations >> 126 MB L2; 4 distinct input frames rotate"},
+                   "l2": "inputs larger than L2: one frame's activations are ~10 GB against a 126 MB L2; 4 distinct frames rotate"},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": ph * pw * 3, "d2h_bytes_per_step": h * w * 3 * 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "api": "Stylization.transfer_stream (pinned H2D + D2H overlapped with compute)",
+                "sync_transfer_ms_per_step": ms_sync},
         "gpu_launches": launches,
         "clocks": clk,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / pk["tflops"], "traffic": None, "peak_source": pk["src"],
-                     "flops_per_frame": fl,
-                     "conv_kernel": {"launches_per_frame": len(layers), "ms_per_frame": conv_ms,
-                                     "executed_tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None}},
+        "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": pk["tflops"], "unit": "TFLOP/s",
+                     "frac": conv_tflops / pk["tflops"], "traffic": traffic, "peak_source": pk["src"],
+                     "kernel": "conv_tc2_kernel / conv_tc_kernel (tcgen05 implicit-GEMM convolution)",
+                     "how": "algorithmic FLOPs of the 30 tensor-core convolutions of one frame (2*Cin*Cout*k*k per output pixel, counted "
+                            "once: the 3 MMAs of the bf16x3 split are not credited) / summed CUDA-event durations of their launches; "
+                            "traffic = DRAM bytes per launch, mean over the frame's conv launches, from profiles/r1_traffic.json",
+                     "launches_per_frame": len(layers), "kernel_ms_per_frame": conv_ms,
+                     "whole_frame": {"achieved": frame_tflops, "frac": frame_tflops / pk["tflops"], "flops_per_frame": fl}},
         "prepass_s": prepass_s,
         "layers": [{"layer": lbl, "ms": round(t, 4), "tflops": round(f / (t * 1e-3) / 1e12, 2) if t > 0 else None}
                    for lbl, t, f in layers],

@@ -31,9 +31,9 @@ def sample_indices(n_frames: int, interval: int = 8):
 def allgather_parts(part: torch.Tensor, group=None) -> torch.Tensor:
     """[5, C] float64 partial statistics -> [world, 5, C] in rank order (NCCL on GPU, gloo on CPU)."""
     world = dist.get_world_size(group)
-    out = torch.empty((world,) + tuple(part.shape), dtype=part.dtype, device=part.device)
-    dist.all_gather_into_tensor(out, part.contiguous(), group=group)
-    return out
+    out = torch.empty((world * part.shape[0],) + tuple(part.shape[1:]), dtype=part.dtype, device=part.device)
+    dist.all_gather_into_tensor(out, part.contiguous(), group=group)      # concatenated along dim 0 (gloo and nccl)
+    return out.view((world,) + tuple(part.shape))
 
 
 def sharded_prepass(fw, sample_frames, rank: int, world: int, group=None):

@@ -69,6 +69,64 @@ class Stylization:
         out = self.transfer_device(frame, crop)
         return out.cpu().numpy()[0]
 
+    def transfer_stream(self, frames, crop=None, depth=3):
+        """Generator over an iterable of uint8 BGR frames of one size: yields exactly what
+        ``transfer(frame, crop)`` returns for each, in order, but pipelined -- the pinned-memory
+        upload of frame i+1 (copy-in stream) and the download of frame i-1 (copy-out stream) overlap the
+        kernels of frame i (current stream).  ``depth`` frames are in flight."""
+        eng = self.model._eng()
+        cur = torch.cuda.current_stream(self.device)
+        s_in, s_out = self._side_streams()
+        slots, pending = [], []
+
+        def finish(slot):
+            slot["ev_out"].synchronize()
+            return slot["host_out"].numpy()[0].copy()
+
+        for i, frame in enumerate(frames):
+            frame = np.ascontiguousarray(frame)
+            if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3:
+                raise ValueError("expected a uint8 HxWx3 BGR image (cv2.imread layout)")
+            H, W = frame.shape[:2]
+            y0, x0, h, w = crop if crop is not None else (0, 0, H, W)
+            if len(slots) < depth:
+                slots.append(dict(host_in=torch.empty((1, H, W, 3), dtype=torch.uint8).pin_memory(),
+                                  dev_in=torch.empty((1, H, W, 3), dtype=torch.uint8, device=self.device),
+                                  net_out=torch.empty((1, 3, H, W), dtype=torch.float32, device=self.device),
+                                  dev_out=torch.empty((1, h, w, 3), dtype=torch.float32, device=self.device),
+                                  host_out=torch.empty((1, h, w, 3), dtype=torch.float32).pin_memory(),
+                                  ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(),
+                                  ev_free=torch.cuda.Event()))
+            slot = slots[i % depth]
+            if len(pending) == depth:                       # this slot's previous frame must be handed out first
+                yield finish(pending.pop(0))
+            if tuple(slot["host_in"].shape[1:3]) != (H, W):
+                raise ValueError("transfer_stream needs frames of one size")
+            slot["host_in"][0].copy_(torch.from_numpy(frame))
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(slot["ev_free"])            # the kernels that read dev_in last time are done
+                slot["dev_in"].copy_(slot["host_in"], non_blocking=True)
+                slot["ev_in"].record(s_in)
+            cur.wait_event(slot["ev_in"])
+            cur.wait_event(slot["ev_out"])                  # dev_out of this slot has been downloaded
+            eng.forward(slot["dev_in"], kind=1, out=slot["net_out"])
+            L.check(L.lib().rrv_postprocess_bgr(slot["net_out"].data_ptr(), 1, H, W, y0, x0, h, w, slot["dev_out"].data_ptr(),
+                                                L.stream()), "rrv_postprocess_bgr")
+            slot["ev_free"].record(cur)
+            slot["ev_done"].record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(slot["ev_done"])
+                slot["host_out"].copy_(slot["dev_out"], non_blocking=True)
+                slot["ev_out"].record(s_out)
+            pending.append(slot)
+        while pending:
+            yield finish(pending.pop(0))
+
+    def _side_streams(self):
+        if not hasattr(self, "_streams"):
+            self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        return self._streams
+
     def transfer_device(self, frame, crop=None):
         eng = self.model._eng()
         y = eng.forward(self._upload(frame), kind=1)

@@ -437,3 +437,95 @@ def test_temporal_loss_and_backward(dev):
         for c in range(3):
             np.add.at(ref[b, c], (iy[b], ix[b]), go[b, c].numpy().astype(np.float64))
     assert rel_linf(x.grad.cpu().numpy(), ref) < 1e-5
+
+
+# ---------------------------------------------------------------------------------- kernel variants / entry point
+
+@pytest.mark.parametrize("tune", [(1, 2, 64), (2, 1, 64), (2, 2, 128)])
+def test_conv_main_loop_variants(L, dev, tune):
+    """rrv_tc_tune2: v1 (one box per tap), v2 with one M tile per weight tile, v2 with the shared-box ups path."""
+    from rerevst_code_b200.engine import ConvW, make_epilogue
+    L.check(L.lib().rrv_tc_tune2(*tune))
+    try:
+        for case in [(1, 40, 24, 64, 64, 3, 0), (2, 36, 20, 128, 128, 3, 0), (1, 48, 32, 128, 64, 3, 1), (1, 40, 16, 256, 256, 3, 1),
+                     (1, 33, 17, 64, 128, 1, 0)]:
+            N, H, W, Cin, Cout, k, ups = case
+            g = torch.Generator().manual_seed(7)
+            hin, win = (H // 2, W // 2) if ups else (H, W)
+            x = torch.randn(N, Cin, hin, win, generator=g)
+            w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+            b = torch.randn(Cout, generator=g) * 0.1
+            cw = ConvW(w.to(dev), b.to(dev), ups=bool(ups))
+            xp = _to_planes(L, x.to(dev))
+            xq = _from_planes(L, xp).cpu()
+            xin = F.interpolate(xq, scale_factor=2, mode="nearest") if ups else xq
+            ref = F.leaky_relu(F.conv2d(xin, w, b, padding=k // 2), 0.2)
+            d = L.Conv()
+            d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = N, H, W, Cin, Cout, k, ups
+            d.in_hi, d.in_lo = L.ptr(xp.hi), L.ptr(xp.lo)
+            d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
+            d.ep = make_epilogue(bias=cw.bias, act=2)
+            d.out_mode = L.OUT_F32_NHWC
+            out = torch.full((N, H, W, Cout), float("nan"), dtype=torch.float32, device=dev)
+            d.out_f32 = out.data_ptr()
+            L.check(L.lib().rrv_conv2d(C.byref(d), L.IMPL_TCGEN05, L.stream()), str(case))
+            assert rel_linf(out.permute(0, 3, 1, 2).cpu(), ref) < 2e-4, (tune, case)
+    finally:
+        L.check(L.lib().rrv_tc_tune2(2, 2, 64))
+
+
+def test_transfer_stream_equals_transfer(L, dev, state_dict):
+    from rerevst_code_b200.framework import Stylization
+    rng = np.random.RandomState(5)
+    smooth = lambda h, w: np.clip(rng.rand(h // 8 + 1, w // 8 + 1, 3).repeat(8, 0).repeat(8, 1)[:h, :w] * 255, 0, 255).astype(np.uint8)
+    fw = Stylization(state_dict, cuda=True)
+    fw.prepare_style(smooth(64, 64))
+    fw.clean()
+    fw.add(smooth(48, 64))
+    fw.compute()
+    frames = [smooth(64, 128) for _ in range(7)]
+    crop = (8, 16, 40, 96)
+    want = [fw.transfer(f, crop=crop) for f in frames]
+    got = list(fw.transfer_stream(iter(frames), crop=crop, depth=3))
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+
+
+def test_generate_real_video_entry(tmp_path, dev, state_dict):
+    """The packaged generate_real_video.main against the same steps done with the CPU oracle."""
+    import cv2
+    from oracle import stylenet
+    from rerevst_code_b200 import generate_real_video as grv
+    rng = np.random.RandomState(9)
+    smooth = lambda h, w: np.clip(rng.rand(h // 8 + 1, w // 8 + 1, 3).repeat(8, 0).repeat(8, 1)[:h, :w] * 255, 0, 255).astype(np.uint8)
+    vid = tmp_path / "inputs" / "clip"
+    vid.mkdir(parents=True)
+    frames = []
+    for i in range(10):
+        f = smooth(40, 56)
+        frames.append(f)
+        cv2.imwrite(str(vid / f"frame_{i:04d}.png"), f)
+    style = smooth(64, 72)
+    cv2.imwrite(str(tmp_path / "style.png"), style)
+    ckpt = tmp_path / "net.pth"
+    torch.save(state_dict, str(ckpt))
+    out_dir = grv.main(style_img=str(tmp_path / "style.png"), content_video=str(vid / "*.png"), checkpoint_path=str(ckpt),
+                       result_frames_path=str(tmp_path / "rf"), result_videos_path=str(tmp_path / "rv"), save_video=False,
+                       verbose=False)
+    import glob
+    order = glob.glob(str(vid / "*.png"))                        # the script's (unsorted) glob order
+    o = stylenet.GlobalOracle(state_dict)
+    o.generate_style_features(stylenet.transform_image(stylenet.numpy2tensor(cv2.imread(str(tmp_path / "style.png")))))
+    o.clean()
+    for s in range((10 - 1) // 8):
+        o.add(stylenet.transform_image(stylenet.numpy2tensor(cv2.imread(order[s * 8]))))
+    o.add(stylenet.transform_image(stylenet.numpy2tensor(cv2.imread(order[-1]))))
+    o.compute()
+    tool = grv.ReshapeTool()
+    for path in order:
+        img = cv2.imread(path)
+        ref = o.transfer(tool.process(img))[64:64 + 40, 64:64 + 56]
+        got = cv2.imread(os.path.join(out_dir, os.path.basename(path))).astype(np.float32)
+        assert got.shape == ref.shape
+        assert float(np.max(np.abs(got - np.clip(np.rint(ref), 0, 255)))) <= 1.0
