@@ -93,10 +93,12 @@ int rrv_pack_weights_tc(const float* w_oihw, int Cin, int Cout, int ksize, int u
 /* Tuning knobs of the tensor-core kernel (defaults 256, 16, 6): widest Cout tile, width of the
  * 128-pixel spatial tile (8..128, power of two), deepest shared-memory pipeline. */
 int rrv_tc_tune(int max_bn, int tile_w, int max_stages);
-/* Main-loop variant (default 2): 1 = one TMA box per tap; 2 = one box per (chunk, dx) shared by the
- * three dy taps, `mt` (1|2) 128-pixel M tiles per weight tile, resident weights when they fit, the
- * four phases of a nearest-x2 convolution in one pass with Cout tiles of at most max_bn_ups. */
-int rrv_tc_tune2(int version, int mt, int max_bn_ups);
+/* Main-loop variant (default 2, 2, 0): version 1 = one TMA box per tap; 2 = one box per (chunk, dx) shared by
+ * the three dy taps, `mt` (1|2) 128-pixel M tiles per weight tile, resident weights when they all fit.
+ * ups_v1 != 0 sends the nearest-x2 convolutions through the version-1 main loop. */
+int rrv_tc_tune2(int version, int mt, int ups_v1);
+/* CTA pairs (tcgen05 cta_group::2, clusters of 2): enabled by default for Cout tiles >= min_bn (128). */
+int rrv_tc_tune_pair(int enable, int min_bn);
 /* fp32 [Cout][Cin][k][k] -> [k*k][Cin_pad][Cout_pad] fp32 (zero padded) for the FFMA path. */
 int rrv_pack_weights_f32(const float* w_oihw, int Cin, int Cout, int ksize, int Cin_pad, int Cout_pad,
                          float* out, void* stream);

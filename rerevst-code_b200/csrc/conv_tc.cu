@@ -50,8 +50,9 @@ struct TcTune {
     int max_stages = 6;     // v1 only
     int version = 2;        // main loop: 1 = one box per tap, 2 = row-reuse / shared weight tiles
     int mt = 2;             // v2: M tiles (128 pixels each) per weight tile
-    int max_bn_ups = 64;    // v2: Cout tile of the nearest-x2 convolutions (4 MT accumulators)
-    int ups_v1 = 1;         // nearest-x2 convolutions use the v1 main loop
+    int ups_v1 = 0;         // 1: nearest-x2 convolutions use the v1 main loop
+    int pair = 1;           // v2: CTA pairs (cta_group::2) for Cout tiles >= pair_min_bn
+    int pair_min_bn = 128;
 };
 TcTune g_tune;
 
@@ -432,35 +433,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 // A and B travel through separate rings (A: a_stages, B: b_slots) filled by one producer thread in
 // consumption order.
 constexpr int MAX_B_SLOTS = 16;
-constexpr int MAX_GRP = 8;
 
 struct Grp {                // one weight tile consumed against the current A box
     int btile;              // index into the [tap][Cout_pad][Cin] blob
-    int acc;                // accumulator of M tile 0 (M tile mt uses acc + mt)
     int arow;               // row offset (in 8-pixel rows) of the A operand inside the box
-    int first;              // first contribution to this accumulator at chunk 0: overwrite
+    int first;              // first contribution to the accumulators at chunk 0: overwrite
 };
 
 struct Tc2Params {
     OutDesc o;
     int N, in_H, in_W;
     int Cout, Cout_pad, kchunks;
-    int ups;                // 1: four output phases per input pixel
-    int MT, halo;
-    int nA;                 // A boxes per chunk (3, or 1 for 1x1)
-    int a_dx[3];
-    int ngrp[3];
-    Grp grp[3][MAX_GRP];
-    int nacc;               // accumulators per tile set = (ups ? 4 : 1) * MT
+    int nph;                // 1, or 4 output phases of a nearest-x2 convolution (each phase is its own tile)
+    int MT;
+    int nA;                 // A boxes per chunk: 3 (3x3), 2 (one ups phase), 1 (1x1)
+    int a_dx[4][3];         // [phase][box]: column offset of the box
+    int a_y0[4];            // [phase]: row offset of the box origin (-1 for 3x3, py - 1 for ups, 0 for 1x1)
+    int ngrp[4][3];
+    Grp grp[4][3][3];
     int tiles_x, tiles_y, n_ntiles, total_tiles;
     int BN, x3;
-    int a_stages, b_slots, b_resident;
-    int a_plane_bytes;      // (16 MT + 2 halo) * 1024
+    int a_stages, b_slots, b_resident, pair;
+    int a_plane_bytes;      // (16 MT + 2) * 1024 (16 MT for 1x1)
     int acc_stride, set_stride, bufs, tmem_cols;
     EpiDev ep;
 };
 
-template <int FLAGS>
+// PAIR: two CTAs of a cluster issue one cta_group::2 MMA per k-slice (256 pixels x BN): each CTA loads its own A box
+// and HALF of the weight rows, so the per-MMA operand fetch drops from 64 + BN/2 to 64 + BN/4 cycles.
+template <int FLAGS, bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -474,7 +475,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t planes = p.x3 ? 2u : 1u;
     const uint32_t a_stage_bytes = planes * (uint32_t)p.a_plane_bytes;
-    const uint32_t b_plane_bytes = (uint32_t)p.BN * 128u;
+    const uint32_t b_plane_bytes = (uint32_t)(PAIR ? p.BN / 2 : p.BN) * 128u;    // a pair splits the weight rows
+    const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
+    const int cta_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;            // persistent worker index
+    const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const uint32_t tx_mult = PAIR ? 2u : 1u;                                     // the leader's barriers count both CTAs' bytes
     const uint32_t b_slot_bytes = planes * b_plane_bytes;
     const uint32_t b_base = smem_base + (uint32_t)p.a_stages * a_stage_bytes;
     const uint32_t tab_off = (uint32_t)p.a_stages * a_stage_bytes + (uint32_t)p.b_slots * b_slot_bytes;
@@ -490,7 +495,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(ptx::smem_u32(&s_tfull[a]), 1);
-            ptx::mbar_init(ptx::smem_u32(&s_tempty[a]), EPI_WARPS);
+            ptx::mbar_init(ptx::smem_u32(&s_tempty[a]), EPI_WARPS * (PAIR ? 2 : 1));
         }
         ptx::fence_barrier_init();
     }
@@ -505,11 +510,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     float* s_tab = reinterpret_cast<float*>(smem_raw + (smem_base - ptx::smem_u32(smem_raw)) + tab_off);
     fill_epilogue_table(s_tab, p.ep, p.Cout, p.Cout_pad, TC_THREADS);
     if (warp == 1) {
-        ptx::tmem_alloc(ptx::smem_u32(&s_tmem_base), (uint32_t)p.tmem_cols);
-        ptx::tmem_relinquish();
+        if (PAIR) {
+            ptx::tmem_alloc_pair(ptx::smem_u32(&s_tmem_base), (uint32_t)p.tmem_cols);
+            ptx::tmem_relinquish_pair();
+        } else {
+            ptx::tmem_alloc(ptx::smem_u32(&s_tmem_base), (uint32_t)p.tmem_cols);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (PAIR) ptx::cluster_sync();          // the peer's barriers are initialised before anyone signals them
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
     const int rows_per_set = 16 * p.MT;
@@ -520,23 +531,31 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
             bool first_set = true;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
                 int t = tile;
+                const int ph = t % p.nph; t /= p.nph;
                 const int n0 = (t % p.n_ntiles) * p.BN; t /= p.n_ntiles;
-                const int x0 = (t % p.tiles_x) * 8; t /= p.tiles_x;
+                const int x0 = ((t % p.tiles_x) * (PAIR ? 2 : 1) + (int)cta_rank) * 8; t /= p.tiles_x;
                 const int y0 = (t % p.tiles_y) * rows_per_set;
                 const int n = t / p.tiles_y;
+                const int by = y0 + p.a_y0[ph];
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     for (int j = 0; j < p.nA; ++j) {
+                        const int bx = x0 + p.a_dx[ph][j];
                         ptx::mbar_wait(ptx::smem_u32(&s_aempty[sa]), pa ^ 1u);
                         const uint32_t full = ptx::smem_u32(&s_afull[sa]);
                         const uint32_t dst = smem_base + (uint32_t)sa * a_stage_bytes;
-                        ptx::mbar_expect_tx(full, a_stage_bytes);
-                        ptx::tma_load_4d(dst, &map_a_hi, full, kc * BK, x0 + p.a_dx[j], y0 - p.halo, n);
-                        if (p.x3) ptx::tma_load_4d(dst + (uint32_t)p.a_plane_bytes, &map_a_lo, full, kc * BK, x0 + p.a_dx[j], y0 - p.halo, n);
+                        if (!PAIR || cta_rank == 0) ptx::mbar_expect_tx(full, tx_mult * a_stage_bytes);
+                        if (PAIR) {
+                            ptx::tma_load_4d_pair(dst, &map_a_hi, full, kc * BK, bx, by, n);
+                            if (p.x3) ptx::tma_load_4d_pair(dst + (uint32_t)p.a_plane_bytes, &map_a_lo, full, kc * BK, bx, by, n);
+                        } else {
+                            ptx::tma_load_4d(dst, &map_a_hi, full, kc * BK, bx, by, n);
+                            if (p.x3) ptx::tma_load_4d(dst + (uint32_t)p.a_plane_bytes, &map_a_lo, full, kc * BK, bx, by, n);
+                        }
                         if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
-                        for (int g = 0; g < p.ngrp[j]; ++g) {
-                            const int btile = p.grp[j][g].btile;
+                        for (int g = 0; g < p.ngrp[ph][j]; ++g) {
+                            const int btile = p.grp[ph][j][g].btile;
                             int slot;
                             if (p.b_resident) {
                                 if (!first_set) continue;
@@ -548,21 +567,28 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             }
                             const uint32_t bfull = ptx::smem_u32(&s_bfull[slot]);
                             const uint32_t bdst = b_base + (uint32_t)slot * b_slot_bytes;
-                            ptx::mbar_expect_tx(bfull, b_slot_bytes);
-                            ptx::tma_load_2d(bdst, &map_b_hi, bfull, kc * BK, btile * p.Cout_pad + n0);
-                            if (p.x3) ptx::tma_load_2d(bdst + b_plane_bytes, &map_b_lo, bfull, kc * BK, btile * p.Cout_pad + n0);
+                            const int brow = btile * p.Cout_pad + n0 + (PAIR ? (int)cta_rank * (p.BN / 2) : 0);
+                            if (!PAIR || cta_rank == 0) ptx::mbar_expect_tx(bfull, tx_mult * b_slot_bytes);
+                            if (PAIR) {
+                                ptx::tma_load_2d_pair(bdst, &map_b_hi, bfull, kc * BK, brow);
+                                if (p.x3) ptx::tma_load_2d_pair(bdst + b_plane_bytes, &map_b_lo, bfull, kc * BK, brow);
+                            } else {
+                                ptx::tma_load_2d(bdst, &map_b_hi, bfull, kc * BK, brow);
+                                if (p.x3) ptx::tma_load_2d(bdst + b_plane_bytes, &map_b_lo, bfull, kc * BK, brow);
+                            }
                         }
                     }
                 }
                 first_set = false;
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        const uint32_t idesc = ptx::make_idesc_bf16(BM, p.BN);
+    } else if (warp == 1 && cta_rank == 0) {
+        // ================= MMA issuer (the leader CTA of a pair) =================
+        const uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * BM : BM, p.BN);
         int sa = 0, sb = 0, as = 0;
         uint32_t pa = 0, pb = 0, aphase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
+            const int ph = tile % p.nph;
             ptx::mbar_wait(ptx::smem_u32(&s_tempty[as]), aphase ^ 1u);
             ptx::tc_fence_after();
             const uint32_t d_set = tmem_base + (uint32_t)(as * p.set_stride);
@@ -570,8 +596,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 for (int j = 0; j < p.nA; ++j) {
                     ptx::mbar_wait(ptx::smem_u32(&s_afull[sa]), pa);
                     const uint32_t a_base = smem_base + (uint32_t)sa * a_stage_bytes;
-                    for (int g = 0; g < p.ngrp[j]; ++g) {
-                        const Grp gr = p.grp[j][g];
+                    for (int g = 0; g < p.ngrp[ph][j]; ++g) {
+                        const Grp gr = p.grp[ph][j][g];
                         int slot;
                         if (p.b_resident) {
                             slot = gr.btile * p.kchunks + kc;
@@ -584,14 +610,22 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         const uint32_t bs = b_base + (uint32_t)slot * b_slot_bytes;
                         const bool overwrite = kc == 0 && gr.first != 0;
                         const uint32_t a0 = a_base + (uint32_t)(gr.arow * 1024);
-                        const uint32_t d0 = d_set + (uint32_t)(gr.acc * p.acc_stride);
+                        const uint32_t d0 = d_set;
                         const uint32_t bempty_bar = ptx::smem_u32(&s_bempty[sb]);
                         if (ptx::elect_one()) {
-                            ptx::mma_kblock(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
-                            if (p.MT == 2)
-                                ptx::mma_kblock(d0 + (uint32_t)p.acc_stride, a0 + 16384u, a0 + 16384u + (uint32_t)p.a_plane_bytes, bs,
-                                                bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
-                            if (!p.b_resident) ptx::mma_commit(bempty_bar);
+                            if (PAIR) {
+                                ptx::mma_kblock_pair(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
+                                if (p.MT == 2)
+                                    ptx::mma_kblock_pair(d0 + (uint32_t)p.acc_stride, a0 + 16384u, a0 + 16384u + (uint32_t)p.a_plane_bytes, bs,
+                                                         bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
+                                ptx::mma_commit_pair(bempty_bar);
+                            } else {
+                                ptx::mma_kblock(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
+                                if (p.MT == 2)
+                                    ptx::mma_kblock(d0 + (uint32_t)p.acc_stride, a0 + 16384u, a0 + 16384u + (uint32_t)p.a_plane_bytes, bs,
+                                                    bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
+                                if (!p.b_resident) ptx::mma_commit(bempty_bar);
+                            }
                         }
                         __syncwarp();
                         if (!p.b_resident) {
@@ -600,8 +634,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     }
                     const uint32_t aempty_bar = ptx::smem_u32(&s_aempty[sa]), tfull_bar = ptx::smem_u32(&s_tfull[as]);
                     if (ptx::elect_one()) {
-                        ptx::mma_commit(aempty_bar);
-                        if (kc == p.kchunks - 1 && j == p.nA - 1) ptx::mma_commit(tfull_bar);
+                        if (PAIR) {
+                            ptx::mma_commit_pair(aempty_bar);
+                            if (kc == p.kchunks - 1 && j == p.nA - 1) ptx::mma_commit_pair(tfull_bar);
+                        } else {
+                            ptx::mma_commit(aempty_bar);
+                            if (kc == p.kchunks - 1 && j == p.nA - 1) ptx::mma_commit(tfull_bar);
+                        }
                     }
                     __syncwarp();
                     if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
@@ -609,7 +648,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             }
             if (++as == p.bufs) { as = 0; aphase ^= 1u; }
         }
-    } else {
+    } else if (warp >= 2) {
         // ================= epilogue (warps 2..9; TMEM lane quadrant = warp % 4) =================
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
@@ -619,38 +658,43 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const EpiDev& e = p.ep;
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
             int t = tile;
+            const int ph = t % p.nph; t /= p.nph;
             const int n0 = (t % p.n_ntiles) * p.BN; t /= p.n_ntiles;
-            const int x0 = (t % p.tiles_x) * 8; t /= p.tiles_x;
+            const int x0 = ((t % p.tiles_x) * (PAIR ? 2 : 1) + (int)cta_rank) * 8; t /= p.tiles_x;
             const int y0 = (t % p.tiles_y) * rows_per_set;
             const int n = t / p.tiles_y;
             ptx::mbar_wait(ptx::smem_u32(&s_tfull[as]), aphase);
             ptx::tc_fence_after();
             const uint32_t t_set = tmem_base + (uint32_t)(as * p.set_stride) + ((uint32_t)(quad * 32) << 16);
-            const int units = p.nacc * nchunks;            // (accumulator, 32-column chunk) pairs
+            const int units = p.MT * nchunks;              // (M tile, 32-column chunk) pairs
             for (int u = half; u < units; u += EPI_WARPS / 4) {
-                const int acc = u / nchunks, ch = u - acc * nchunks;
-                const int phase = acc / p.MT, mt = acc - phase * p.MT;
+                const int mt = u / nchunks, ch = u - mt * nchunks;
                 const int iy = y0 + 16 * mt + ty, ix = x0 + tx;
                 const bool valid = iy < p.in_H && ix < p.in_W;
-                const int oy = p.ups ? 2 * iy + (phase >> 1) : iy;
-                const int ox = p.ups ? 2 * ix + (phase & 1) : ix;
-                epilogue_chunk<FLAGS>(p.o, e, s_tab, p.Cout_pad, t_set + (uint32_t)(acc * p.acc_stride + ch * 32), valid, n, oy, ox,
+                const int oy = p.nph == 4 ? 2 * iy + (ph >> 1) : iy;
+                const int ox = p.nph == 4 ? 2 * ix + (ph & 1) : ix;
+                epilogue_chunk<FLAGS>(p.o, e, s_tab, p.Cout_pad, t_set + (uint32_t)(mt * p.acc_stride + ch * 32), valid, n, oy, ox,
                                       n0 + ch * 32, ch * 32, p.BN);
             }
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&s_tempty[as]));
+            if (lane == 0) {
+                if (PAIR) ptx::mbar_arrive_cluster(ptx::smem_u32(&s_tempty[as]), 0u);     // the leader's MMA warp waits for both CTAs
+                else ptx::mbar_arrive(ptx::smem_u32(&s_tempty[as]));
+            }
             if (++as == p.bufs) { as = 0; aphase ^= 1u; }
         }
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (PAIR) ptx::cluster_sync();
+    else __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+        if (PAIR) ptx::tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+        else ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
 }
 
@@ -782,17 +826,41 @@ int launch_tc1(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, co
     return check_launch("conv_tc_kernel");
 }
 
-template <int FLAGS>
-int launch_tc2(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
-               const CUtensorMap& mb_lo, const Tc2Params& d) {
+template <int FLAGS, bool PAIR>
+int launch_tc2p(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
+                const CUtensorMap& mb_lo, const Tc2Params& d) {
     static bool attr_set = false;
     if (!attr_set) {
-        const cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        const cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<FLAGS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         RRV_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(conv_tc2_kernel): %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    conv_tc2_kernel<FLAGS><<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, d);
+    if (!PAIR) {
+        conv_tc2_kernel<FLAGS, PAIR><<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, d);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<FLAGS, PAIR>, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        RRV_REQUIRE(e == cudaSuccess, "cudaLaunchKernelEx(conv_tc2_kernel, cluster 2): %s", cudaGetErrorString(e));
+    }
     return check_launch("conv_tc2_kernel");
+}
+
+template <int FLAGS>
+int launch_tc2(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
+               const CUtensorMap& mb_lo, const Tc2Params& d) {
+    return d.pair ? launch_tc2p<FLAGS, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d)
+                  : launch_tc2p<FLAGS, false>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
 }
 
 int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
@@ -805,32 +873,32 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     d.Cout = p->Cout;
     d.Cout_pad = cout_pad_of(p->Cout);
     d.kchunks = p->Cin / BK;
-    d.ups = ups;
     d.x3 = p->in_lo != nullptr;
-    d.halo = (p->ksize == 3) ? 1 : 0;
+    d.nph = ups ? 4 : 1;
+    const int halo = (p->ksize == 3) ? 1 : 0;
     const int planes = d.x3 ? 2 : 1;
-    const int nph = ups ? 4 : 1;
-    const int btiles = ups ? 16 : p->ksize * p->ksize;
+    const int btiles = ups ? 16 : p->ksize * p->ksize;     // weight tiles per chunk in the blob
+    const int btiles_tile = ups ? 4 : btiles;               // ... of which one tile (= one phase) uses this many
 
     // ---- tile shape: Cout tile BN, M tiles per weight tile MT ----
-    int max_bn = ups ? std::min(g_tune.max_bn_ups, g_tune.max_bn) : g_tune.max_bn;
-    int BN = std::min(d.Cout_pad, max_bn);
+    int BN = std::min(d.Cout_pad, g_tune.max_bn);
     while (BN > 16 && d.Cout_pad % BN != 0) BN -= 16;
     int MT = std::max(1, std::min(g_tune.mt, 2));
     if (d.in_H <= 16) MT = 1;
     const int budget = SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES;
     int a_stage = 0, b_slot = 0;
     // all weight tiles resident beats sharing them between two M tiles: prefer MT = 1 if that is what fits
-    if (MT == 2 && BN == d.Cout_pad && btiles * d.kchunks <= MAX_B_SLOTS) {
+    const bool resident_shape = !ups && BN == d.Cout_pad && btiles * d.kchunks <= MAX_B_SLOTS;
+    if (MT == 2 && resident_shape) {
         const int b_all = btiles * d.kchunks * planes * BN * 128;
-        const int a2 = planes * (32 + 2 * d.halo) * 1024, a1 = planes * (16 + 2 * d.halo) * 1024;
+        const int a2 = planes * (32 + 2 * halo) * 1024, a1 = planes * (16 + 2 * halo) * 1024;
         if (b_all + 2 * a2 > budget && b_all + 2 * a1 <= budget) MT = 1;
     }
     for (;;) {
         const int acc_stride = (BN + 31) / 32 * 32;
-        a_stage = planes * (16 * MT + 2 * d.halo) * 1024;
+        a_stage = planes * (16 * MT + 2 * halo) * 1024;
         b_slot = planes * BN * 128;
-        const bool tmem_ok = nph * MT * acc_stride <= 512;
+        const bool tmem_ok = MT * acc_stride <= 512;
         const bool smem_ok = 2 * a_stage + 2 * b_slot <= budget;
         if (tmem_ok && smem_ok) break;
         if (MT > 1) { MT = 1; continue; }
@@ -839,18 +907,21 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         while (BN > 16 && d.Cout_pad % BN != 0) BN -= 16;
     }
     d.BN = BN; d.MT = MT;
+    // CTA pairs everywhere except where all weight tiles can stay resident (the 64 -> 64 layers)
+    const bool resident_fits = resident_shape && btiles * d.kchunks * b_slot + 2 * a_stage <= budget;
+    d.pair = (g_tune.pair && !resident_fits && BN >= g_tune.pair_min_bn && BN % 32 == 0 && num_sms() % 2 == 0) ? 1 : 0;
+    if (d.pair) b_slot /= 2;
     d.n_ntiles = d.Cout_pad / BN;
     d.acc_stride = (BN + 31) / 32 * 32;
-    d.nacc = nph * MT;
-    d.set_stride = d.nacc * d.acc_stride;
+    d.set_stride = MT * d.acc_stride;
     d.bufs = 2 * d.set_stride <= 512 ? 2 : 1;
     d.tmem_cols = 32;
     while (d.tmem_cols < d.bufs * d.set_stride) d.tmem_cols *= 2;
-    d.a_plane_bytes = (16 * MT + 2 * d.halo) * 1024;
+    d.a_plane_bytes = (16 * MT + 2 * halo) * 1024;
 
     // ---- rings ----
     const int b_all = btiles * d.kchunks;
-    if (d.n_ntiles == 1 && b_all <= MAX_B_SLOTS && b_all * b_slot + 2 * a_stage <= budget) {
+    if (!d.pair && resident_fits && d.n_ntiles == 1) {
         d.b_resident = 1;
         d.b_slots = b_all;
         d.a_stages = std::min(4, (budget - b_all * b_slot) / a_stage);
@@ -865,40 +936,36 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
             break;
         }
     }
+    (void)btiles_tile;
 
     // ---- which weight tiles meet which A box ----
     if (p->ksize == 1) {
-        d.nA = 1; d.a_dx[0] = 0; d.ngrp[0] = 1;
-        d.grp[0][0] = Grp{0, 0, 0, 1};
+        d.nA = 1; d.a_dx[0][0] = 0; d.a_y0[0] = 0; d.ngrp[0][0] = 1;
+        d.grp[0][0][0] = Grp{0, 0, 1};
     } else if (!ups) {
-        d.nA = 3;
+        // box = rows y0-1 .. y0+16MT, columns x0+dx ..; tap (dy, dx) reads it from row dy
+        d.nA = 3; d.a_y0[0] = -1;
         for (int j = 0; j < 3; ++j) {
-            d.a_dx[j] = j - 1; d.ngrp[j] = 3;
-            for (int dy = 0; dy < 3; ++dy) d.grp[j][dy] = Grp{dy * 3 + j, 0, dy, (j == 0 && dy == 0) ? 1 : 0};
+            d.a_dx[0][j] = j - 1; d.ngrp[0][j] = 3;
+            for (int dy = 0; dy < 3; ++dy) d.grp[0][j][dy] = Grp{dy * 3 + j, dy, (j == 0 && dy == 0) ? 1 : 0};
         }
     } else {
-        d.nA = 3;
-        bool seen[4] = {false, false, false, false};
-        for (int j = 0; j < 3; ++j) {
-            const int ox = j - 1;
-            d.a_dx[j] = ox;
-            int g = 0;
-            for (int py = 0; py < 2; ++py)
-                for (int a = 0; a < 2; ++a)
-                    for (int px = 0; px < 2; ++px) {
-                        const int b = ox - (px - 1);
-                        if (b < 0 || b > 1) continue;
-                        const int ph = py * 2 + px;
-                        d.grp[j][g++] = Grp{ph * 4 + a * 2 + b, ph * MT, py - 1 + a + 1, seen[ph] ? 0 : 1};
-                        seen[ph] = true;
-                    }
-            d.ngrp[j] = g;
+        // phase (py, px) of the nearest-x2 convolution = a 2x2 convolution over the low-res input with taps at rows
+        // py-1+a and columns px-1+b: box origin row y0+py-1, boxes at columns x0+px-1 and x0+px, tap a reads from row a
+        d.nA = 2;
+        for (int ph = 0; ph < 4; ++ph) {
+            const int py = ph >> 1, px = ph & 1;
+            d.a_y0[ph] = py - 1;
+            for (int b = 0; b < 2; ++b) {
+                d.a_dx[ph][b] = px - 1 + b; d.ngrp[ph][b] = 2;
+                for (int a = 0; a < 2; ++a) d.grp[ph][b][a] = Grp{ph * 4 + a * 2 + b, a, (a == 0 && b == 0) ? 1 : 0};
+            }
         }
     }
 
-    d.tiles_x = ceil_div(d.in_W, 8);
+    d.tiles_x = ceil_div(d.in_W, d.pair ? 16 : 8);          // a pair takes two horizontally adjacent tiles
     d.tiles_y = ceil_div(d.in_H, 16 * MT);
-    const long long total = (long long)d.N * d.tiles_y * d.tiles_x * d.n_ntiles;
+    const long long total = (long long)d.N * d.tiles_y * d.tiles_x * d.n_ntiles * d.nph;
     RRV_REQUIRE(total < (1LL << 31), "rrv_conv2d: too many tiles");
     d.total_tiles = (int)total;
     d.ep = make_epi(p->ep, p->Cout);
@@ -908,19 +975,20 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     const int rows = btiles * d.Cout_pad;
     const uint16_t* w_hi = (const uint16_t*)p->w_tc;
     const uint16_t* w_lo = w_hi + (long long)rows * p->Cin;
-    const int box_rows = 16 * MT + 2 * d.halo;
+    const int box_rows = 16 * MT + 2 * halo;
     if (encode_act_map(&ma_hi, p->in_hi, d.N, d.in_H, d.in_W, p->Cin, 8, box_rows)) return 1;
-    if (encode_w_map(&mb_hi, w_hi, rows, p->Cin, BN)) return 1;
+    const int b_box = d.pair ? BN / 2 : BN;
+    if (encode_w_map(&mb_hi, w_hi, rows, p->Cin, b_box)) return 1;
     if (d.x3) {
         if (encode_act_map(&ma_lo, p->in_lo, d.N, d.in_H, d.in_W, p->Cin, 8, box_rows)) return 1;
-        if (encode_w_map(&mb_lo, w_lo, rows, p->Cin, BN)) return 1;
+        if (encode_w_map(&mb_lo, w_lo, rows, p->Cin, b_box)) return 1;
     } else {
         ma_lo = ma_hi;
         mb_lo = mb_hi;
     }
     const int smem = d.a_stages * a_stage + d.b_slots * b_slot + d.Cout_pad * TAB_BYTES + 1024;
     const int flags = epi_flags(p->ep);
-    const int grid = std::min(d.total_tiles, num_sms());
+    const int grid = d.pair ? 2 * std::min(d.total_tiles, num_sms() / 2) : std::min(d.total_tiles, num_sms());
     switch (flags) {
         case 0: return launch_tc2<0>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
         case EPI_N1: return launch_tc2<EPI_N1>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
@@ -944,14 +1012,19 @@ int tc_tune(int max_bn, int tile_w, int max_stages) {
     return 0;
 }
 
-int tc_tune2(int version, int mt, int max_bn_ups) {
+int tc_tune_pair(int enable, int min_bn) {
+    RRV_REQUIRE(min_bn >= 32 && min_bn <= 256 && min_bn % 32 == 0, "rrv_tc_tune_pair: min_bn must be a multiple of 32 in [32, 256]");
+    g_tune.pair = enable ? 1 : 0;
+    g_tune.pair_min_bn = min_bn;
+    return 0;
+}
+
+int tc_tune2(int version, int mt, int ups_v1) {
     RRV_REQUIRE(version == 1 || version == 2, "rrv_tc_tune2: version must be 1 or 2");
     RRV_REQUIRE(mt == 1 || mt == 2, "rrv_tc_tune2: mt must be 1 or 2");
-    RRV_REQUIRE(max_bn_ups >= 16 && max_bn_ups <= 128 && max_bn_ups % 16 == 0, "rrv_tc_tune2: max_bn_ups must be a multiple of 16 in [16, 128]");
     g_tune.version = version;
     g_tune.mt = mt;
-    g_tune.max_bn_ups = max_bn_ups;
-    g_tune.ups_v1 = max_bn_ups <= 64 ? 1 : 0;     // asking for a wider ups tile selects the v2 ups path
+    g_tune.ups_v1 = ups_v1 ? 1 : 0;
     return 0;
 }
 
@@ -995,8 +1068,6 @@ int conv2d_tc(const rrv_conv* p, cudaStream_t st) {
         RRV_REQUIRE(p->out_mode != RRV_OUT_F32_NCHW || p->out_C > 0, "rrv_conv2d: out_C must be set for NCHW output");
     }
 
-    // nearest-x2 layers: per-phase tiles with the widest Cout tile (v1) beat the shared-box main loop,
-    // whose 4 MT accumulators cap the Cout tile at 64 (operand fetch cost per MMA ~ 64 + N/2 cycles)
     if (g_tune.version == 2 && !(ups && g_tune.ups_v1)) return conv2d_tc2(p, st);
 
     TcParams d;

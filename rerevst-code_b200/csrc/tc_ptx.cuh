@@ -142,6 +142,90 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// ---- CTA pairs (cta_group::2) ----------------------------------------------------------------------
+// Two CTAs of one cluster (same TPC) execute one 256-row MMA: each holds its own 128 rows of A and half of
+// the B rows in its shared memory, and its 128 accumulator rows in its own TMEM.  Shared-memory addresses
+// carry the CTA rank in bit 24; clearing it addresses the same offset in the leader CTA (rank 0).
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 remote;\n\t"
+        "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t"
+        "}\n"
+        ::"r"(bar), "r"(cta)
+        : "memory");
+}
+// TMA loads of a CTA pair: data lands in the executing CTA, the bytes are counted on the LEADER's barrier.
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"((uint64_t)tmap), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"((uint64_t)tmap), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void mma_bf16_lo_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
+        "}\n"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128)
+        : "memory");
+}
+__device__ __forceinline__ void mma_kblock_pair(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
+                                                uint32_t idesc, bool x3, bool overwrite) {
+    const uint32_t ah = desc_lo_sw128(a_hi), al = desc_lo_sw128(a_lo), bh = desc_lo_sw128(b_hi), bl = desc_lo_sw128(b_lo);
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) {
+        mma_bf16_lo_pair(d_tmem, ah + 2 * k, bh + 2 * k, idesc, (overwrite && k == 0) ? 0u : 1u);
+        if (x3) {
+            mma_bf16_lo_pair(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1u);
+            mma_bf16_lo_pair(d_tmem, al + 2 * k, bh + 2 * k, idesc, 1u);
+        }
+    }
+}
+// Arrives on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs have completed.
+__device__ __forceinline__ void mma_commit_pair(uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b16 mask;\n\t"
+        "mov.b16 mask, 3;\n\t"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], mask;\n\t"
+        "}\n"
+        ::"r"(bar)
+        : "memory");
+}
+
 // One warp reads its 32 TMEM lanes x 32 consecutive fp32 columns: thread i <- lane (base + i).
 // Split into issue and wait so independent global loads can be put in flight in between; the wait
 // names the registers as in/out operands so no use of them can be scheduled above it.

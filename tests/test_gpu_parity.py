@@ -441,11 +441,13 @@ def test_temporal_loss_and_backward(dev):
 
 # ---------------------------------------------------------------------------------- kernel variants / entry point
 
-@pytest.mark.parametrize("tune", [(1, 2, 64), (2, 1, 64), (2, 2, 128)])
+@pytest.mark.parametrize("tune", [(1, 2, 0, 1), (2, 1, 0, 1), (2, 2, 1, 1), (2, 2, 0, 0)])
 def test_conv_main_loop_variants(L, dev, tune):
-    """rrv_tc_tune2: v1 (one box per tap), v2 with one M tile per weight tile, v2 with the shared-box ups path."""
+    """rrv_tc_tune2 / rrv_tc_tune_pair: v1 (one box per tap), v2 with one M tile per weight tile, ups through v1,
+    v2 without CTA pairs (the defaults -- v2, two M tiles, pairs -- run in every other test)."""
     from rerevst_code_b200.engine import ConvW, make_epilogue
-    L.check(L.lib().rrv_tc_tune2(*tune))
+    L.check(L.lib().rrv_tc_tune2(*tune[:3]))
+    L.check(L.lib().rrv_tc_tune_pair(tune[3], 128))
     try:
         for case in [(1, 40, 24, 64, 64, 3, 0), (2, 36, 20, 128, 128, 3, 0), (1, 48, 32, 128, 64, 3, 1), (1, 40, 16, 256, 256, 3, 1),
                      (1, 33, 17, 64, 128, 1, 0)]:
@@ -471,7 +473,8 @@ def test_conv_main_loop_variants(L, dev, tune):
             L.check(L.lib().rrv_conv2d(C.byref(d), L.IMPL_TCGEN05, L.stream()), str(case))
             assert rel_linf(out.permute(0, 3, 1, 2).cpu(), ref) < 2e-4, (tune, case)
     finally:
-        L.check(L.lib().rrv_tc_tune2(2, 2, 64))
+        L.check(L.lib().rrv_tc_tune2(2, 2, 0))
+        L.check(L.lib().rrv_tc_tune_pair(1, 128))
 
 
 def test_transfer_stream_equals_transfer(L, dev, state_dict):
