@@ -97,7 +97,7 @@ int rrv_tc_tune(int max_bn, int tile_w, int max_stages);
  * the three dy taps, `mt` (1|2) 128-pixel M tiles per weight tile, resident weights when they all fit.
  * ups_v1 != 0 sends the nearest-x2 convolutions through the version-1 main loop. */
 int rrv_tc_tune2(int version, int mt, int ups_v1);
-/* CTA pairs (tcgen05 cta_group::2, clusters of 2): enabled by default for Cout tiles >= min_bn (128). */
+/* CTA pairs (tcgen05 cta_group::2, clusters of 2): enabled by default for Cout tiles >= min_bn (64). */
 int rrv_tc_tune_pair(int enable, int min_bn);
 /* fp32 [Cout][Cin][k][k] -> [k*k][Cin_pad][Cout_pad] fp32 (zero padded) for the FFMA path. */
 int rrv_pack_weights_f32(const float* w_oihw, int Cin, int Cout, int ksize, int Cin_pad, int Cout_pad,

@@ -52,7 +52,7 @@ struct TcTune {
     int mt = 2;             // v2: M tiles (128 pixels each) per weight tile
     int ups_v1 = 0;         // 1: nearest-x2 convolutions use the v1 main loop
     int pair = 1;           // v2: CTA pairs (cta_group::2) for Cout tiles >= pair_min_bn
-    int pair_min_bn = 128;
+    int pair_min_bn = 64;   // (<= 64 also overrides resident weights: measured faster on the 64 -> 64 layers)
 };
 TcTune g_tune;
 
@@ -909,7 +909,7 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     d.BN = BN; d.MT = MT;
     // CTA pairs everywhere except where all weight tiles can stay resident (the 64 -> 64 layers)
     const bool resident_fits = resident_shape && btiles * d.kchunks * b_slot + 2 * a_stage <= budget;
-    d.pair = (g_tune.pair && !resident_fits && BN >= g_tune.pair_min_bn && BN % 32 == 0 && num_sms() % 2 == 0) ? 1 : 0;
+    d.pair = (g_tune.pair && (!resident_fits || g_tune.pair_min_bn <= 64) && BN >= g_tune.pair_min_bn && BN % 32 == 0 && num_sms() % 2 == 0) ? 1 : 0;
     if (d.pair) b_slot /= 2;
     d.n_ntiles = d.Cout_pad / BN;
     d.acc_stride = (BN + 31) / 32 * 32;

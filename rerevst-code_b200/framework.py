@@ -92,7 +92,6 @@ class Stylization:
             if len(slots) < depth:
                 slots.append(dict(host_in=torch.empty((1, H, W, 3), dtype=torch.uint8).pin_memory(),
                                   dev_in=torch.empty((1, H, W, 3), dtype=torch.uint8, device=self.device),
-                                  net_out=torch.empty((1, 3, H, W), dtype=torch.float32, device=self.device),
                                   dev_out=torch.empty((1, h, w, 3), dtype=torch.float32, device=self.device),
                                   host_out=torch.empty((1, h, w, 3), dtype=torch.float32).pin_memory(),
                                   ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(),
@@ -109,8 +108,8 @@ class Stylization:
                 slot["ev_in"].record(s_in)
             cur.wait_event(slot["ev_in"])
             cur.wait_event(slot["ev_out"])                  # dev_out of this slot has been downloaded
-            eng.forward(slot["dev_in"], kind=1, out=slot["net_out"])
-            L.check(L.lib().rrv_postprocess_bgr(slot["net_out"].data_ptr(), 1, H, W, y0, x0, h, w, slot["dev_out"].data_ptr(),
+            net_out = eng.forward_graphed(slot["dev_in"], kind=1)
+            L.check(L.lib().rrv_postprocess_bgr(net_out.data_ptr(), 1, H, W, y0, x0, h, w, slot["dev_out"].data_ptr(),
                                                 L.stream()), "rrv_postprocess_bgr")
             slot["ev_free"].record(cur)
             slot["ev_done"].record(cur)
@@ -129,7 +128,7 @@ class Stylization:
 
     def transfer_device(self, frame, crop=None):
         eng = self.model._eng()
-        y = eng.forward(self._upload(frame), kind=1)
+        y = eng.forward_graphed(self._upload(frame), kind=1)
         N, _, H, W = y.shape
         y0, x0, h, w = crop if crop is not None else (0, 0, H, W)
         out = torch.empty((N, h, w, 3), dtype=torch.float32, device=self.device)

@@ -474,7 +474,7 @@ def test_conv_main_loop_variants(L, dev, tune):
             assert rel_linf(out.permute(0, 3, 1, 2).cpu(), ref) < 2e-4, (tune, case)
     finally:
         L.check(L.lib().rrv_tc_tune2(2, 2, 0))
-        L.check(L.lib().rrv_tc_tune_pair(1, 128))
+        L.check(L.lib().rrv_tc_tune_pair(1, 64))
 
 
 def test_transfer_stream_equals_transfer(L, dev, state_dict):

@@ -1,0 +1,67 @@
+"""Dev tool: time single convolution layers of the 1080p frame under different kernel tunings.
+usage: python tools/layer_bench.py  (prints ms per layer per tuning)"""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from rerevst_code_b200 import _lib as L
+from rerevst_code_b200.engine import ConvW, Planes, make_epilogue
+
+dev = torch.device("cuda", 0)
+LAYERS = {  # name: (H, W, Cin, Cout, k, ups)
+    "c64_64": (1216, 2048, 64, 64, 3, 0), "c64_128": (608, 1024, 64, 128, 3, 0), "c128_128": (608, 1024, 128, 128, 3, 0),
+    "c256_256": (304, 512, 256, 256, 3, 0), "c256_512": (152, 256, 256, 512, 3, 0), "c512_64": (152, 256, 512, 64, 3, 0),
+    "c64_512": (152, 256, 64, 512, 3, 0), "u512_256": (304, 512, 512, 256, 3, 1), "u256_128": (608, 1024, 256, 128, 3, 1),
+    "u128_64": (1216, 2048, 128, 64, 3, 1), "s128_64": (608, 1024, 128, 64, 1, 0), "head": (1216, 2048, 64, 3, 3, 0),
+}
+
+
+def bench(name, tunings, iters=5):
+    H, W, Cin, Cout, k, ups = LAYERS[name]
+    g = torch.Generator().manual_seed(0)
+    hin, win = (H // 2, W // 2) if ups else (H, W)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    cw = ConvW(w.to(dev), b.to(dev), ups=bool(ups))
+    xp = Planes(1, hin, win, Cin, True, dev)
+    xp.hi.normal_()
+    xp.lo.zero_()
+    d = L.Conv()
+    d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = 1, H, W, Cin, Cout, k, ups
+    d.in_hi, d.in_lo = L.ptr(xp.hi), L.ptr(xp.lo)
+    d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
+    d.ep = make_epilogue(bias=cw.bias, act=1)
+    if Cout % 8 == 0:
+        o = Planes(1, H, W, Cout, True, dev)
+        d.out_mode, d.out_hi, d.out_lo = L.OUT_PLANES, L.ptr(o.hi), L.ptr(o.lo)
+    else:
+        o = torch.empty((1, 3, H, W), dtype=torch.float32, device=dev)
+        d.out_mode, d.out_f32, d.out_C = L.OUT_F32_NCHW, o.data_ptr(), 3
+    flops = 2.0 * Cin * Cout * k * k * H * W
+    res = []
+    for label, (ver, mt, upsv1, pair, minbn, maxbn) in tunings.items():
+        L.check(L.lib().rrv_tc_tune2(ver, mt, upsv1))
+        L.check(L.lib().rrv_tc_tune_pair(pair, minbn))
+        L.check(L.lib().rrv_tc_tune(maxbn, 16, 6))
+        for _ in range(2):
+            L.check(L.lib().rrv_conv2d(C.byref(d), 1, L.stream()))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            L.check(L.lib().rrv_conv2d(C.byref(d), 1, L.stream()))
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        res.append(f"{label}={ms:.3f}ms({flops / ms / 1e9:.0f}TF)")
+    print(f"{name:10s} " + "  ".join(res), flush=True)
+
+
+if __name__ == "__main__":
+    T = {"default": (2, 2, 0, 1, 128, 256), "pair64": (2, 2, 0, 1, 64, 256), "nopair": (2, 2, 0, 0, 128, 256),
+         "mt1": (2, 1, 0, 1, 128, 256), "bn128": (2, 2, 0, 1, 128, 128), "v1": (1, 2, 1, 0, 128, 256)}
+    names = sys.argv[1:] or list(LAYERS)
+    for n in names:
+        bench(n, T)
