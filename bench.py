@@ -32,6 +32,10 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
+# stdout carries exactly ONE JSON line: everything libraries print there (e.g. NCCL's version banner) goes to stderr
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
 SIZES = {"1080p": (1080, 1920), "720p": (720, 1280), "256": (256, 256)}
 METRIC = "stylized frames/sec at 1080p (1/2/4/8 B200) + % conv roofline"
 
@@ -169,7 +173,7 @@ def run_reference(args):
                              "sample": f"TransformerNet.forward on a {sh}x{pw} strip (1/{round(1 / frac)} of a padded frame) per step, "
                                        f"scaled by pixel count; torch {torch.__version__} CPU"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------ our arm
@@ -368,7 +372,7 @@ def main():
         line["parity"] = {"rel_linf_vs_cpu_oracle_full_frame": err, "tolerance": 1e-3 if args.precision == "x3" else None}
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -99,6 +99,9 @@ int rrv_tc_tune(int max_bn, int tile_w, int max_stages);
 int rrv_tc_tune2(int version, int mt, int ups_v1);
 /* CTA pairs (tcgen05 cta_group::2, clusters of 2): enabled by default for Cout tiles >= min_bn (64). */
 int rrv_tc_tune_pair(int enable, int min_bn);
+/* Merge the three dy taps of a 3x3 convolution into one MMA along N (N = 3 Cout) when 3 Cout <= 256: the
+ * 64-channel layers, whose cost is the A-operand fetch.  Enabled by default. */
+int rrv_tc_tune_merge(int enable);
 /* fp32 [Cout][Cin][k][k] -> [k*k][Cin_pad][Cout_pad] fp32 (zero padded) for the FFMA path. */
 int rrv_pack_weights_f32(const float* w_oihw, int Cin, int Cout, int ksize, int Cin_pad, int Cout_pad,
                          float* out, void* stream);

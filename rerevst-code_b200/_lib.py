@@ -46,6 +46,7 @@ SIGNATURES = {
     "rrv_tc_tune": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "rrv_tc_tune2": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "rrv_tc_tune_pair": (C.c_int, [C.c_int, C.c_int]),
+    "rrv_tc_tune_merge": (C.c_int, [C.c_int]),
     "rrv_pack_weights_f32": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rrv_first_layer": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rrv_maxpool2x2": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),

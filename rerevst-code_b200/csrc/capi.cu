@@ -35,6 +35,7 @@ int pack_weights_tc(const float* w, int Cin, int Cout, int ksize, int ups, void*
 int tc_tune(int max_bn, int tile_w, int max_stages);
 int tc_tune2(int version, int mt, int ups_v1);
 int tc_tune_pair(int enable, int min_bn);
+int tc_tune_merge(int enable);
 int first_layer(const void* src, int src_kind, int gray, int N, int H, int W, const float* w, const float* bias,
                 void* out_hi, void* out_lo, float* out_f32, cudaStream_t st);
 int maxpool2x2(const void* in_hi, const void* in_lo, int N, int H, int W, int C, void* out_hi, void* out_lo, cudaStream_t st);
@@ -84,6 +85,7 @@ int rrv_pack_weights_tc(const float* w, int Cin, int Cout, int ksize, int ups, v
 int rrv_tc_tune(int max_bn, int tile_w, int max_stages) { return tc_tune(max_bn, tile_w, max_stages); }
 int rrv_tc_tune2(int version, int mt, int ups_v1) { return tc_tune2(version, mt, ups_v1); }
 int rrv_tc_tune_pair(int enable, int min_bn) { return tc_tune_pair(enable, min_bn); }
+int rrv_tc_tune_merge(int enable) { return tc_tune_merge(enable); }
 int rrv_pack_weights_f32(const float* w, int Cin, int Cout, int ksize, int Cin_pad, int Cout_pad, float* out, void* stream) {
     return pack_weights_f32(w, Cin, Cout, ksize, Cin_pad, Cout_pad, out, ST(stream));
 }

@@ -39,7 +39,8 @@ constexpr int BM = 128;          // output pixels per tile (= TMEM lanes)
 constexpr int BK = 64;           // channels per k-step (128-byte rows)
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int MAX_STAGES = 8;
-constexpr int EPI_WARPS = 8;      // two per TMEM lane quadrant, alternating 32-column chunks
+constexpr int EPI_WARPS = 8;      // two per TMEM lane quadrant, alternating CW-column chunks
+constexpr int CW = 32;            // epilogue chunk width (accumulator columns per tcgen05.ld)
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TAB_BYTES = 48;     // per-channel epilogue constants: 11 floats (+1 pad)
 constexpr int SMEM_LIMIT = 227 * 1024 - 1024;   // dynamic part: the opt-in maximum minus the static barriers
@@ -51,6 +52,7 @@ struct TcTune {
     int version = 2;        // main loop: 1 = one box per tap, 2 = row-reuse / shared weight tiles
     int mt = 2;             // v2: M tiles (128 pixels each) per weight tile
     int ups_v1 = 0;         // 1: nearest-x2 convolutions use the v1 main loop
+    int dym = 1;            // v2: merge the three dy taps along N when 3 Cout_pad <= 256 (the 64-channel layers)
     int pair = 1;           // v2: CTA pairs (cta_group::2) for Cout tiles >= pair_min_bn
     int pair_min_bn = 64;   // (<= 64 also overrides resident weights: measured faster on the 64 -> 64 layers)
 };
@@ -157,15 +159,30 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
     lo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
 }
 
-__device__ __forceinline__ void store_group(const OutDesc& p, const float* v, int n, int oy, int ox, int c0, int nvalid) {
-    const long long pix = ((long long)n * p.H + oy) * p.W + ox;
+// Where one accumulator row (= one output pixel) goes, computed once per (tile, M tile) by each epilogue thread.
+struct PixCtx {
+    long long out_off;      // element offset of the pixel's channel 0 in an NHWC output: ((n H + oy) W + ox) Cout
+    long long res_off;      // same for the residual tensor (half resolution when res_shift = 1)
+    int n, oy, ox;
+    bool valid;
+};
+
+__device__ __forceinline__ PixCtx make_pix(const OutDesc& o, const EpiDev& e, int n, int oy, int ox, bool valid) {
+    PixCtx px;
+    px.n = n; px.oy = oy; px.ox = ox; px.valid = valid;
+    px.out_off = (((long long)n * o.H + oy) * o.W + ox) * o.Cout;
+    px.res_off = e.res_hi ? (long long)n * e.res_batch_stride + ((long long)(oy >> e.res_shift) * e.res_W + (ox >> e.res_shift)) * e.C : 0;
+    return px;
+}
+
+__device__ __forceinline__ void store_group(const OutDesc& p, const float* v, const PixCtx& px, int c0, int nvalid) {
     if (p.out_mode == RRV_OUT_PLANES) {
         uint4 hi, lo;
         split8(v, hi, lo);
-        *reinterpret_cast<uint4*>(p.out_hi + pix * p.Cout + c0) = hi;
-        if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + pix * p.Cout + c0) = lo;
+        *reinterpret_cast<uint4*>(p.out_hi + px.out_off + c0) = hi;
+        if (p.out_lo) *reinterpret_cast<uint4*>(p.out_lo + px.out_off + c0) = lo;
     } else if (p.out_mode == RRV_OUT_F32_NHWC) {
-        float* o = p.out_f32 + pix * p.Cout + c0;
+        float* o = p.out_f32 + px.out_off + c0;
         if (nvalid == 8) {
             *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -178,106 +195,144 @@ __device__ __forceinline__ void store_group(const OutDesc& p, const float* v, in
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             if (k < nvalid && c0 + k < p.out_C)
-                p.out_f32[(((long long)n * p.out_C + c0 + k) * p.H + oy) * p.W + ox] = v[k];
+                p.out_f32[(((long long)px.n * p.out_C + c0 + k) * p.H + px.oy) * p.W + px.ox] = v[k];
     }
 }
 
-// One 32-channel chunk of one accumulator row (= one output pixel) through the fused pointwise
-// chain: bias -> act -> saved-stat norm -> + residual -> saved-stat norm -> AdaIN -> store.
-// cb = first global output channel of the chunk, col0 = its first column inside the Cout tile.
-// FLAGS >= 0 fixes the set of stages at compile time (EPI_* bits); FLAGS < 0 reads it from `e`.
+// The fused pointwise chain on 8 consecutive channels starting at c0: bias -> act -> saved-stat norm ->
+// + residual (rh/rl = the 8 hi / lo residual halves) -> saved-stat norm -> AdaIN.
 template <int FLAGS>
-__device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e, const float* s_tab, int ts, uint32_t taddr,
-                                               bool valid, int n, int oy, int ox, int cb, int col0, int BN) {
+__device__ __forceinline__ void chain8(const EpiDev& e, const float* s_tab, int ts, int c0, const uint32_t* acc, float* x,
+                                       const uint4& rh, const uint4& rl, bool res_packed, const PixCtx& px, int Cout) {
     const bool has_n1 = FLAGS >= 0 ? (FLAGS & EPI_N1) != 0 : e.norm1 != nullptr;
     const bool has_res = FLAGS >= 0 ? (FLAGS & EPI_RES) != 0 : e.res_hi != nullptr;
     const bool has_n2 = FLAGS >= 0 ? (FLAGS & EPI_N2) != 0 : e.norm2 != nullptr;
     const bool has_aff = FLAGS >= 0 ? (FLAGS & EPI_AFF) != 0 : e.affine != nullptr;
     const bool res_x3 = e.res_lo != nullptr;
-    uint32_t r[32];
-    ptx::tmem_ld32_issue(taddr, r);
-    // the residual of the whole chunk goes in flight while the TMEM load completes
-    uint4 rh[4], rl[4];
-    const bool full32 = cb + 32 <= o.Cout && col0 + 32 <= BN;
-    long long res_off = 0;
-    if (has_res) {
-        res_off = (long long)n * e.res_batch_stride + ((long long)(oy >> e.res_shift) * e.res_W + (ox >> e.res_shift)) * e.C;
-        if (valid && full32) {
+    float k0[8], k1[8];
+    lds8(s_tab + T_BIAS * ts + c0, k0);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                rh[g] = *reinterpret_cast<const uint4*>(e.res_hi + res_off + cb + g * 8);
-                if (res_x3) rl[g] = *reinterpret_cast<const uint4*>(e.res_lo + res_off + cb + g * 8);
+    for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[i]) + k0[i];
+    if (e.act == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.0f);
+    } else if (e.act == 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = x[i] > 0.0f ? x[i] : 0.2f * x[i];
+    }
+    if (has_n1) {
+        lds8(s_tab + T_M1 * ts + c0, k0);
+        lds8(s_tab + T_R1 * ts + c0, k1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = (x[i] - k0[i]) * k1[i];
+        lds8(s_tab + T_LO1 * ts + c0, k0);
+        lds8(s_tab + T_HI1 * ts + c0, k1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fminf(k1[i], fmaxf(k0[i], x[i]));
+    }
+    if (has_res) {
+        if (res_packed) {
+            const uint32_t hw[4] = {rh.x, rh.y, rh.z, rh.w};
+            const uint32_t lw[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float a = __uint_as_float(hw[i] << 16), b = __uint_as_float(hw[i] & 0xffff0000u);
+                if (res_x3) {
+                    a += __uint_as_float(lw[i] << 16);
+                    b += __uint_as_float(lw[i] & 0xffff0000u);
+                }
+                x[2 * i] += a;
+                x[2 * i + 1] += b;
+            }
+        } else {                              // ragged channel tail (never on the per-frame path)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int cc = c0 + i;
+                float rr = cc < Cout ? bf16_to_f32(e.res_hi[px.res_off + cc]) : 0.0f;
+                if (res_x3 && cc < Cout) rr += bf16_to_f32(e.res_lo[px.res_off + cc]);
+                x[i] += rr;
             }
         }
     }
-    ptx::tmem_ld32_wait(r);
-    if (!valid) return;
+    if (has_n2) {
+        lds8(s_tab + T_M2 * ts + c0, k0);
+        lds8(s_tab + T_R2 * ts + c0, k1);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+        for (int i = 0; i < 8; ++i) x[i] = (x[i] - k0[i]) * k1[i];
+        lds8(s_tab + T_LO2 * ts + c0, k0);
+        lds8(s_tab + T_HI2 * ts + c0, k1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fminf(k1[i], fmaxf(k0[i], x[i]));
+    }
+    if (has_aff) {
+        lds8(s_tab + T_SCALE * ts + c0, k0);
+        lds8(s_tab + T_SHIFT * ts + c0, k1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = x[i] * k0[i] + k1[i];
+    }
+}
+
+// One CW-channel chunk of one accumulator row (= one output pixel): tcgen05.ld, the fused chain, the stores.
+// cb = first global output channel of the chunk, col0 = its first column inside the Cout tile.
+// FLAGS >= 0 fixes the set of stages at compile time (EPI_* bits); FLAGS < 0 reads it from `e`.
+// DYM: the accumulator holds the three dy taps side by side (columns [0,Cp) [Cp,2Cp) [2Cp,3Cp), Cp = ts) for INPUT
+// row = lane; output row `lane` = tap0[lane] + tap1[lane+1] + tap2[lane+2] (the lanes of one quadrant are
+// consecutive rows of one image column).
+template <int FLAGS, bool DYM>
+__device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e, const float* s_tab, int ts, uint32_t taddr,
+                                               const PixCtx& px, int cb, int col0, int BN) {
+    const bool has_res = FLAGS >= 0 ? (FLAGS & EPI_RES) != 0 : e.res_hi != nullptr;
+    uint32_t r[CW];
+    ptx::tmem_ld32_issue(taddr, r);
+    if (DYM) {
+        uint32_t r1[CW], r2[CW];
+        ptx::tmem_ld32_issue(taddr + (uint32_t)ts, r1);
+        ptx::tmem_ld32_issue(taddr + (uint32_t)(2 * ts), r2);
+        ptx::tmem_ld32_wait(r);
+        ptx::tmem_ld32_wait(r1);
+        ptx::tmem_ld32_wait(r2);
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+            const float a = __uint_as_float(r[i]);
+            const float b = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[i]), 1);
+            const float c = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[i]), 2);
+            r[i] = __float_as_uint((a + b) + c);
+        }
+    }
+    // the residual of the whole chunk goes in flight while the TMEM load completes
+    uint4 rh[CW / 8], rl[CW / 8];
+    const bool full = cb + CW <= o.Cout && col0 + CW <= BN;        // warp-uniform
+    if (has_res && px.valid && full) {
+#pragma unroll
+        for (int g = 0; g < CW / 8; ++g) {
+            rh[g] = *reinterpret_cast<const uint4*>(e.res_hi + px.res_off + cb + g * 8);
+            if (e.res_lo) rl[g] = *reinterpret_cast<const uint4*>(e.res_lo + px.res_off + cb + g * 8);
+        }
+    }
+    if (!DYM) ptx::tmem_ld32_wait(r);
+    if (!px.valid) return;
+    if (full && o.out_mode == RRV_OUT_PLANES) {
+        // fast path (every per-frame layer but the RGB head): no per-group range checks, planes output
+        uint16_t* oh = o.out_hi + px.out_off + cb;
+        uint16_t* ol = o.out_lo ? o.out_lo + px.out_off + cb : nullptr;
+#pragma unroll
+        for (int g = 0; g < CW / 8; ++g) {
+            float x[8];
+            chain8<FLAGS>(e, s_tab, ts, cb + g * 8, r + g * 8, x, rh[g], rl[g], true, px, o.Cout);
+            uint4 hi, lo;
+            split8(x, hi, lo);
+            *reinterpret_cast<uint4*>(oh + g * 8) = hi;
+            if (ol) *reinterpret_cast<uint4*>(ol + g * 8) = lo;
+        }
+        return;
+    }
+#pragma unroll
+    for (int g = 0; g < CW / 8; ++g) {
         const int c0 = cb + g * 8;
         if (c0 >= o.Cout || col0 + g * 8 >= BN) continue;
-        float x[8], k0[8], k1[8];
-        lds8(s_tab + T_BIAS * ts + c0, k0);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(r[g * 8 + i]) + k0[i];
-        if (e.act == 1) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.0f);
-        } else if (e.act == 2) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = x[i] > 0.0f ? x[i] : 0.2f * x[i];
-        }
-        if (has_n1) {
-            lds8(s_tab + T_M1 * ts + c0, k0);
-            lds8(s_tab + T_R1 * ts + c0, k1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = (x[i] - k0[i]) * k1[i];
-            lds8(s_tab + T_LO1 * ts + c0, k0);
-            lds8(s_tab + T_HI1 * ts + c0, k1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = fminf(k1[i], fmaxf(k0[i], x[i]));
-        }
-        if (has_res) {
-            if (full32) {
-                const uint32_t hw[4] = {rh[g].x, rh[g].y, rh[g].z, rh[g].w};
-                const uint32_t lw[4] = {rl[g].x, rl[g].y, rl[g].z, rl[g].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float a = __uint_as_float(hw[i] << 16), b = __uint_as_float(hw[i] & 0xffff0000u);
-                    if (res_x3) {
-                        a += __uint_as_float(lw[i] << 16);
-                        b += __uint_as_float(lw[i] & 0xffff0000u);
-                    }
-                    x[2 * i] += a;
-                    x[2 * i + 1] += b;
-                }
-            } else {                              // ragged channel tail (never on the per-frame path)
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int cc = c0 + i;
-                    float rr = cc < o.Cout ? bf16_to_f32(e.res_hi[res_off + cc]) : 0.0f;
-                    if (res_x3 && cc < o.Cout) rr += bf16_to_f32(e.res_lo[res_off + cc]);
-                    x[i] += rr;
-                }
-            }
-        }
-        if (has_n2) {
-            lds8(s_tab + T_M2 * ts + c0, k0);
-            lds8(s_tab + T_R2 * ts + c0, k1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = (x[i] - k0[i]) * k1[i];
-            lds8(s_tab + T_LO2 * ts + c0, k0);
-            lds8(s_tab + T_HI2 * ts + c0, k1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = fminf(k1[i], fmaxf(k0[i], x[i]));
-        }
-        if (has_aff) {
-            lds8(s_tab + T_SCALE * ts + c0, k0);
-            lds8(s_tab + T_SHIFT * ts + c0, k1);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = x[i] * k0[i] + k1[i];
-        }
-        store_group(o, x, n, oy, ox, c0, c0 + 8 <= o.Cout ? 8 : o.Cout - c0);
+        float x[8];
+        chain8<FLAGS>(e, s_tab, ts, c0, r + g * 8, x, rh[g], rl[g], full, px, o.Cout);
+        store_group(o, x, px, c0, c0 + 8 <= o.Cout ? 8 : o.Cout - c0);
     }
 }
 
@@ -339,7 +394,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 for (int t = 0; t < p.ntaps; ++t) {
                     int oy, ox;
                     tap_offset(p, c, t, oy, ox);
-                    const int brow = (c.phase * p.ntaps + t) * p.Cout_pad + c.n0;
+                    const int tb = (p.nphase == 1 && p.ksize == 3) ? (t % 3) * 3 + t / 3 : t;     // blob order is dx-major for 3x3
+                    const int brow = (c.phase * p.ntaps + tb) * p.Cout_pad + c.n0;
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         ptx::mbar_wait(ptx::smem_u32(&s_empty[stage]), phase ^ 1u);
                         const uint32_t full = ptx::smem_u32(&s_full[stage]);
@@ -388,7 +444,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int half = (warp - 2) >> 2;                 // which 32-column chunks this warp takes
         const int m = quad * 32 + lane;
         const int ty = m >> p.tw_shift, tx = m & ((1 << p.tw_shift) - 1);
-        const int nchunks = (p.BN + 31) / 32;
+        const int nchunks = (p.BN + CW - 1) / CW;
         const EpiDev& e = p.ep;
         int as = 0;
         uint32_t aphase = 0;
@@ -401,8 +457,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             ptx::mbar_wait(ptx::smem_u32(&s_tfull[as]), aphase);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t)(as * p.acc_stride) + ((uint32_t)(quad * 32) << 16);
+            const PixCtx px = make_pix(p.o, e, c.n, oy, ox, valid);
             for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4)
-                epilogue_chunk<FLAGS>(p.o, e, s_tab, p.Cout_pad, taddr + (uint32_t)(ch * 32), valid, c.n, oy, ox, c.n0 + ch * 32, ch * 32, p.BN);
+                epilogue_chunk<FLAGS, false>(p.o, e, s_tab, p.Cout_pad, taddr + (uint32_t)(ch * CW), px, c.n0 + ch * CW, ch * CW, p.BN);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&s_tempty[as]));
@@ -452,7 +509,10 @@ struct Tc2Params {
     int ngrp[4][3];
     Grp grp[4][3][3];
     int tiles_x, tiles_y, n_ntiles, total_tiles;
-    int BN, x3;
+    int BN, x3;             // BN = N of the MMA (3 Cout_pad when the dy taps are merged)
+    int BNe;                // output channels per tile (= BN, or Cout_pad when merged)
+    int b_tile_rows;        // blob rows per weight tile index (Cout_pad, or 3 Cout_pad when merged)
+    int dym;                // dy taps merged along N: M tile = 32 rows x 4 columns, one quadrant per column
     int a_stages, b_slots, b_resident, pair;
     int a_plane_bytes;      // (16 MT + 2) * 1024 (16 MT for 1x1)
     int acc_stride, set_stride, bufs, tmem_cols;
@@ -523,7 +583,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
-    const int rows_per_set = 16 * p.MT;
+    const int rows_per_set = p.dym ? 30 : 16 * p.MT;         // merged taps: 32 input rows give 30 output rows
+    const int cols_per_tile = p.dym ? 4 * p.MT : 8;
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -535,7 +596,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 int t = tile;
                 const int ph = t % p.nph; t /= p.nph;
                 const int n0 = (t % p.n_ntiles) * p.BN; t /= p.n_ntiles;
-                const int x0 = ((t % p.tiles_x) * (PAIR ? 2 : 1) + (int)cta_rank) * 8; t /= p.tiles_x;
+                const int x0 = ((t % p.tiles_x) * (PAIR ? 2 : 1) + (int)cta_rank) * cols_per_tile; t /= p.tiles_x;
                 const int y0 = (t % p.tiles_y) * rows_per_set;
                 const int n = t / p.tiles_y;
                 const int by = y0 + p.a_y0[ph];
@@ -546,12 +607,17 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         const uint32_t full = ptx::smem_u32(&s_afull[sa]);
                         const uint32_t dst = smem_base + (uint32_t)sa * a_stage_bytes;
                         if (!PAIR || cta_rank == 0) ptx::mbar_expect_tx(full, tx_mult * a_stage_bytes);
-                        if (PAIR) {
-                            ptx::tma_load_4d_pair(dst, &map_a_hi, full, kc * BK, bx, by, n);
-                            if (p.x3) ptx::tma_load_4d_pair(dst + (uint32_t)p.a_plane_bytes, &map_a_lo, full, kc * BK, bx, by, n);
-                        } else {
-                            ptx::tma_load_4d(dst, &map_a_hi, full, kc * BK, bx, by, n);
-                            if (p.x3) ptx::tma_load_4d(dst + (uint32_t)p.a_plane_bytes, &map_a_lo, full, kc * BK, bx, by, n);
+                        const int nbox = p.dym ? 4 * p.MT : 1;            // merged taps: one 32-row x 1-column box per quadrant
+                        for (int q = 0; q < nbox; ++q) {
+                            const uint32_t dq = dst + (uint32_t)q * 4096u;
+                            const int cx = bx + q;
+                            if (PAIR) {
+                                ptx::tma_load_4d_pair(dq, &map_a_hi, full, kc * BK, cx, by, n);
+                                if (p.x3) ptx::tma_load_4d_pair(dq + (uint32_t)p.a_plane_bytes, &map_a_lo, full, kc * BK, cx, by, n);
+                            } else {
+                                ptx::tma_load_4d(dq, &map_a_hi, full, kc * BK, cx, by, n);
+                                if (p.x3) ptx::tma_load_4d(dq + (uint32_t)p.a_plane_bytes, &map_a_lo, full, kc * BK, cx, by, n);
+                            }
                         }
                         if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
                         for (int g = 0; g < p.ngrp[ph][j]; ++g) {
@@ -567,7 +633,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             }
                             const uint32_t bfull = ptx::smem_u32(&s_bfull[slot]);
                             const uint32_t bdst = b_base + (uint32_t)slot * b_slot_bytes;
-                            const int brow = btile * p.Cout_pad + n0 + (PAIR ? (int)cta_rank * (p.BN / 2) : 0);
+                            const int brow = btile * p.b_tile_rows + n0 + (PAIR ? (int)cta_rank * (p.BN / 2) : 0);
                             if (!PAIR || cta_rank == 0) ptx::mbar_expect_tx(bfull, tx_mult * b_slot_bytes);
                             if (PAIR) {
                                 ptx::tma_load_2d_pair(bdst, &map_b_hi, bfull, kc * BK, brow);
@@ -618,7 +684,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                                 if (p.MT == 2)
                                     ptx::mma_kblock_pair(d0 + (uint32_t)p.acc_stride, a0 + 16384u, a0 + 16384u + (uint32_t)p.a_plane_bytes, bs,
                                                          bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
-                                ptx::mma_commit_pair(bempty_bar);
+                                if (!p.b_resident) ptx::mma_commit_pair(bempty_bar);
                             } else {
                                 ptx::mma_kblock(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
                                 if (p.MT == 2)
@@ -653,30 +719,32 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
         const int m = quad * 32 + lane;
-        const int ty = m >> 3, tx = m & 7;
-        const int nchunks = (p.BN + 31) / 32;
+        const int ty = p.dym ? lane : (m >> 3), tx = p.dym ? quad : (m & 7);
+        const int nchunks = (p.BNe + CW - 1) / CW;
         const EpiDev& e = p.ep;
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
             int t = tile;
             const int ph = t % p.nph; t /= p.nph;
-            const int n0 = (t % p.n_ntiles) * p.BN; t /= p.n_ntiles;
-            const int x0 = ((t % p.tiles_x) * (PAIR ? 2 : 1) + (int)cta_rank) * 8; t /= p.tiles_x;
+            const int n0 = (t % p.n_ntiles) * p.BNe; t /= p.n_ntiles;
+            const int x0 = ((t % p.tiles_x) * (PAIR ? 2 : 1) + (int)cta_rank) * cols_per_tile; t /= p.tiles_x;
             const int y0 = (t % p.tiles_y) * rows_per_set;
             const int n = t / p.tiles_y;
             ptx::mbar_wait(ptx::smem_u32(&s_tfull[as]), aphase);
             ptx::tc_fence_after();
             const uint32_t t_set = tmem_base + (uint32_t)(as * p.set_stride) + ((uint32_t)(quad * 32) << 16);
-            const int units = p.MT * nchunks;              // (M tile, 32-column chunk) pairs
-            for (int u = half; u < units; u += EPI_WARPS / 4) {
-                const int mt = u / nchunks, ch = u - mt * nchunks;
-                const int iy = y0 + 16 * mt + ty, ix = x0 + tx;
-                const bool valid = iy < p.in_H && ix < p.in_W;
+            for (int mt = 0; mt < p.MT; ++mt) {
+                const int iy = y0 + (p.dym ? 0 : 16 * mt) + ty, ix = x0 + (p.dym ? 4 * mt : 0) + tx;
+                const bool valid = iy < p.in_H && ix < p.in_W && (!p.dym || ty < 30);
                 const int oy = p.nph == 4 ? 2 * iy + (ph >> 1) : iy;
                 const int ox = p.nph == 4 ? 2 * ix + (ph & 1) : ix;
-                epilogue_chunk<FLAGS>(p.o, e, s_tab, p.Cout_pad, t_set + (uint32_t)(mt * p.acc_stride + ch * 32), valid, n, oy, ox,
-                                      n0 + ch * 32, ch * 32, p.BN);
+                const PixCtx px = make_pix(p.o, e, n, oy, ox, valid);
+                const uint32_t ta = t_set + (uint32_t)(mt * p.acc_stride);
+                for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4) {
+                    if (p.dym) epilogue_chunk<FLAGS, true>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, ch * CW, p.BNe);
+                    else epilogue_chunk<FLAGS, false>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, ch * CW, p.BNe);
+                }
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -698,7 +766,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     }
 }
 
-// ---- weight repack: OIHW fp32 -> [tap][Cout_pad][Cin] bf16 hi / lo ---------------------------------
+// ---- weight repack: OIHW fp32 -> [tap][Cout_pad][Cin] bf16 hi / lo (3x3: tap = dx*3 + dy) -------------
 __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ w, int Cin, int Cout, int Cout_pad, int ksize,
                                                       int ups, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
     const int ntaps = ups ? 16 : ksize * ksize;
@@ -711,7 +779,8 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ 
         if (co < Cout) {
             const float* wk = w + ((long long)co * Cin + ci) * ksize * ksize;
             if (!ups) {
-                v = wk[t];
+                // 3x3: blob tap t = dx * 3 + dy (dx-major, so the three dy taps of one dx are adjacent rows)
+                v = ksize == 3 ? wk[(t % 3) * 3 + t / 3] : wk[t];
             } else {
                 // phase (py,px), tap (a,b): sum of the 3x3 weights whose upsampled sample falls on
                 // low-res offset (py-1+a, px-1+b):  floor((py + dy - 1) / 2) == py - 1 + a
@@ -880,91 +949,132 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     const int btiles = ups ? 16 : p->ksize * p->ksize;     // weight tiles per chunk in the blob
     const int btiles_tile = ups ? 4 : btiles;               // ... of which one tile (= one phase) uses this many
 
-    // ---- tile shape: Cout tile BN, M tiles per weight tile MT ----
-    int BN = std::min(d.Cout_pad, g_tune.max_bn);
-    while (BN > 16 && d.Cout_pad % BN != 0) BN -= 16;
-    int MT = std::max(1, std::min(g_tune.mt, 2));
-    if (d.in_H <= 16) MT = 1;
     const int budget = SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES;
-    int a_stage = 0, b_slot = 0;
-    // all weight tiles resident beats sharing them between two M tiles: prefer MT = 1 if that is what fits
-    const bool resident_shape = !ups && BN == d.Cout_pad && btiles * d.kchunks <= MAX_B_SLOTS;
-    if (MT == 2 && resident_shape) {
-        const int b_all = btiles * d.kchunks * planes * BN * 128;
-        const int a2 = planes * (32 + 2 * halo) * 1024, a1 = planes * (16 + 2 * halo) * 1024;
-        if (b_all + 2 * a2 > budget && b_all + 2 * a1 <= budget) MT = 1;
-    }
-    for (;;) {
-        const int acc_stride = (BN + 31) / 32 * 32;
-        a_stage = planes * (16 * MT + 2 * halo) * 1024;
-        b_slot = planes * BN * 128;
-        const bool tmem_ok = MT * acc_stride <= 512;
-        const bool smem_ok = 2 * a_stage + 2 * b_slot <= budget;
-        if (tmem_ok && smem_ok) break;
-        if (MT > 1) { MT = 1; continue; }
-        RRV_REQUIRE(BN > 16, "rrv_conv2d(tcgen05 v2): no tile shape fits (Cout=%d)", p->Cout);
-        BN -= 16;
-        while (BN > 16 && d.Cout_pad % BN != 0) BN -= 16;
-    }
-    d.BN = BN; d.MT = MT;
-    // CTA pairs everywhere except where all weight tiles can stay resident (the 64 -> 64 layers)
-    const bool resident_fits = resident_shape && btiles * d.kchunks * b_slot + 2 * a_stage <= budget;
-    d.pair = (g_tune.pair && (!resident_fits || g_tune.pair_min_bn <= 64) && BN >= g_tune.pair_min_bn && BN % 32 == 0 && num_sms() % 2 == 0) ? 1 : 0;
-    if (d.pair) b_slot /= 2;
-    d.n_ntiles = d.Cout_pad / BN;
-    d.acc_stride = (BN + 31) / 32 * 32;
-    d.set_stride = MT * d.acc_stride;
-    d.bufs = 2 * d.set_stride <= 512 ? 2 : 1;
-    d.tmem_cols = 32;
-    while (d.tmem_cols < d.bufs * d.set_stride) d.tmem_cols *= 2;
-    d.a_plane_bytes = (16 * MT + 2 * halo) * 1024;
-
-    // ---- rings ----
-    const int b_all = btiles * d.kchunks;
-    if (!d.pair && resident_fits && d.n_ntiles == 1) {
-        d.b_resident = 1;
-        d.b_slots = b_all;
-        d.a_stages = std::min(4, (budget - b_all * b_slot) / a_stage);
-    } else {
-        d.b_resident = 0;
-        d.a_stages = 2; d.b_slots = 2;
-        int rem = budget - 2 * a_stage - 2 * b_slot;
-        for (;;) {
-            if (d.b_slots < 4 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
-            if (d.a_stages < 3 && rem >= a_stage) { ++d.a_stages; rem -= a_stage; continue; }
-            if (d.b_slots < 8 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
-            break;
-        }
-    }
-    (void)btiles_tile;
-
-    // ---- which weight tiles meet which A box ----
-    if (p->ksize == 1) {
-        d.nA = 1; d.a_dx[0][0] = 0; d.a_y0[0] = 0; d.ngrp[0][0] = 1;
-        d.grp[0][0][0] = Grp{0, 0, 1};
-    } else if (!ups) {
-        // box = rows y0-1 .. y0+16MT, columns x0+dx ..; tap (dy, dx) reads it from row dy
-        d.nA = 3; d.a_y0[0] = -1;
-        for (int j = 0; j < 3; ++j) {
-            d.a_dx[0][j] = j - 1; d.ngrp[0][j] = 3;
-            for (int dy = 0; dy < 3; ++dy) d.grp[0][j][dy] = Grp{dy * 3 + j, dy, (j == 0 && dy == 0) ? 1 : 0};
-        }
-    } else {
-        // phase (py, px) of the nearest-x2 convolution = a 2x2 convolution over the low-res input with taps at rows
-        // py-1+a and columns px-1+b: box origin row y0+py-1, boxes at columns x0+px-1 and x0+px, tap a reads from row a
-        d.nA = 2;
-        for (int ph = 0; ph < 4; ++ph) {
-            const int py = ph >> 1, px = ph & 1;
-            d.a_y0[ph] = py - 1;
-            for (int b = 0; b < 2; ++b) {
-                d.a_dx[ph][b] = px - 1 + b; d.ngrp[ph][b] = 2;
-                for (int a = 0; a < 2; ++a) d.grp[ph][b][a] = Grp{ph * 4 + a * 2 + b, a, (a == 0 && b == 0) ? 1 : 0};
+    int a_stage = 0, b_slot = 0, box_w = 8, box_rows = 0;
+    d.dym = (g_tune.dym && p->ksize == 3 && !ups && 3 * d.Cout_pad <= 256 && d.Cout_pad % 32 == 0 && d.in_H >= 8) ? 1 : 0;
+    if (d.dym) {
+        // ---- merged dy taps: N = 3 Cout_pad, M tile = 32 input rows x 4 columns (one TMEM lane quadrant per column) ----
+        const int MT = 1;
+        d.MT = MT;
+        d.BN = 3 * d.Cout_pad; d.BNe = d.Cout_pad; d.b_tile_rows = 3 * d.Cout_pad;
+        d.n_ntiles = 1;
+        d.pair = (g_tune.pair && num_sms() % 2 == 0) ? 1 : 0;
+        a_stage = planes * MT * 16384;
+        b_slot = planes * d.BN * 128 / (d.pair ? 2 : 1);
+        d.a_plane_bytes = MT * 16384;
+        d.acc_stride = (d.BN + 31) / 32 * 32;
+        d.set_stride = MT * d.acc_stride;
+        d.bufs = 2 * d.set_stride <= 512 ? 2 : 1;
+        d.tmem_cols = 32;
+        while (d.tmem_cols < d.bufs * d.set_stride) d.tmem_cols *= 2;
+        const int b_all = 3 * d.kchunks;
+        if (b_all <= MAX_B_SLOTS && b_all * b_slot + 2 * a_stage <= budget) {
+            d.b_resident = 1; d.b_slots = b_all;
+            d.a_stages = std::min(6, (budget - b_all * b_slot) / a_stage);
+        } else {
+            d.b_resident = 0; d.a_stages = 2; d.b_slots = 2;
+            int rem = budget - 2 * a_stage - 2 * b_slot;
+            RRV_REQUIRE(rem >= 0, "rrv_conv2d(tcgen05 v2): merged-tap tile does not fit shared memory");
+            for (;;) {
+                if (d.b_slots < 3 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
+                if (d.a_stages < 4 && rem >= a_stage) { ++d.a_stages; rem -= a_stage; continue; }
+                break;
             }
         }
-    }
+        d.nA = 3; d.a_y0[0] = -1;
+        for (int j = 0; j < 3; ++j) {
+            d.a_dx[0][j] = j - 1; d.ngrp[0][j] = 1;
+            d.grp[0][j][0] = Grp{j, 0, j == 0 ? 1 : 0};       // weight tile j = the three dy taps of dx = j - 1
+        }
+        box_w = 1; box_rows = 32;
+        d.tiles_x = ceil_div(d.in_W, 4 * MT * (d.pair ? 2 : 1));
+        d.tiles_y = ceil_div(d.in_H, 30);
+    } else {
+        // ---- tile shape: Cout tile BN, M tiles per weight tile MT ----
+        int BN = std::min(d.Cout_pad, g_tune.max_bn);
+        while (BN > 16 && d.Cout_pad % BN != 0) BN -= 16;
+        int MT = std::max(1, std::min(g_tune.mt, 2));
+        if (d.in_H <= 16) MT = 1;
+        // all weight tiles resident beats sharing them between two M tiles: prefer MT = 1 if that is what fits
+        const bool resident_shape = !ups && BN == d.Cout_pad && btiles * d.kchunks <= MAX_B_SLOTS;
+        if (MT == 2 && resident_shape) {
+            const int b_all = btiles * d.kchunks * planes * BN * 128;
+            const int a2 = planes * (32 + 2 * halo) * 1024, a1 = planes * (16 + 2 * halo) * 1024;
+            if (b_all + 2 * a2 > budget && b_all + 2 * a1 <= budget) MT = 1;
+        }
+        for (;;) {
+            const int acc_stride = (BN + 31) / 32 * 32;
+            a_stage = planes * (16 * MT + 2 * halo) * 1024;
+            b_slot = planes * BN * 128;
+            const bool tmem_ok = MT * acc_stride <= 512;
+            const bool smem_ok = 2 * a_stage + 2 * b_slot <= budget;
+            if (tmem_ok && smem_ok) break;
+            if (MT > 1) { MT = 1; continue; }
+            RRV_REQUIRE(BN > 16, "rrv_conv2d(tcgen05 v2): no tile shape fits (Cout=%d)", p->Cout);
+            BN -= 16;
+            while (BN > 16 && d.Cout_pad % BN != 0) BN -= 16;
+        }
+        d.BN = BN; d.MT = MT; d.BNe = BN; d.b_tile_rows = d.Cout_pad;
+        // CTA pairs everywhere except where all weight tiles can stay resident (the 64 -> 64 layers)
+        const bool resident_fits = resident_shape && btiles * d.kchunks * b_slot + 2 * a_stage <= budget;
+        d.pair = (g_tune.pair && (!resident_fits || g_tune.pair_min_bn <= 64) && BN >= g_tune.pair_min_bn && BN % 32 == 0 && num_sms() % 2 == 0) ? 1 : 0;
+        if (d.pair) b_slot /= 2;
+        d.n_ntiles = d.Cout_pad / BN;
+        d.acc_stride = (BN + 31) / 32 * 32;
+        d.set_stride = MT * d.acc_stride;
+        d.bufs = 2 * d.set_stride <= 512 ? 2 : 1;
+        d.tmem_cols = 32;
+        while (d.tmem_cols < d.bufs * d.set_stride) d.tmem_cols *= 2;
+        d.a_plane_bytes = (16 * MT + 2 * halo) * 1024;
 
-    d.tiles_x = ceil_div(d.in_W, d.pair ? 16 : 8);          // a pair takes two horizontally adjacent tiles
-    d.tiles_y = ceil_div(d.in_H, 16 * MT);
+        // ---- rings ----
+        const int b_all = btiles * d.kchunks;
+        if (!d.pair && resident_fits && d.n_ntiles == 1) {
+            d.b_resident = 1;
+            d.b_slots = b_all;
+            d.a_stages = std::min(4, (budget - b_all * b_slot) / a_stage);
+        } else {
+            d.b_resident = 0;
+            d.a_stages = 2; d.b_slots = 2;
+            int rem = budget - 2 * a_stage - 2 * b_slot;
+            for (;;) {
+                if (d.b_slots < 4 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
+                if (d.a_stages < 3 && rem >= a_stage) { ++d.a_stages; rem -= a_stage; continue; }
+                if (d.b_slots < 8 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
+                break;
+            }
+        }
+        (void)btiles_tile;
+
+        // ---- which weight tiles meet which A box ----
+        if (p->ksize == 1) {
+            d.nA = 1; d.a_dx[0][0] = 0; d.a_y0[0] = 0; d.ngrp[0][0] = 1;
+            d.grp[0][0][0] = Grp{0, 0, 1};
+        } else if (!ups) {
+            // box = rows y0-1 .. y0+16MT, columns x0+dx ..; tap (dy, dx) reads it from row dy
+            d.nA = 3; d.a_y0[0] = -1;
+            for (int j = 0; j < 3; ++j) {
+                d.a_dx[0][j] = j - 1; d.ngrp[0][j] = 3;
+                for (int dy = 0; dy < 3; ++dy) d.grp[0][j][dy] = Grp{j * 3 + dy, dy, (j == 0 && dy == 0) ? 1 : 0};
+            }
+        } else {
+            // phase (py, px) of the nearest-x2 convolution = a 2x2 convolution over the low-res input with taps at rows
+            // py-1+a and columns px-1+b: box origin row y0+py-1, boxes at columns x0+px-1 and x0+px, tap a reads from row a
+            d.nA = 2;
+            for (int ph = 0; ph < 4; ++ph) {
+                const int py = ph >> 1, px = ph & 1;
+                d.a_y0[ph] = py - 1;
+                for (int b = 0; b < 2; ++b) {
+                    d.a_dx[ph][b] = px - 1 + b; d.ngrp[ph][b] = 2;
+                    for (int a = 0; a < 2; ++a) d.grp[ph][b][a] = Grp{ph * 4 + a * 2 + b, a, (a == 0 && b == 0) ? 1 : 0};
+                }
+            }
+        }
+
+        box_w = 8; box_rows = 16 * MT + 2 * halo;
+        d.tiles_x = ceil_div(d.in_W, d.pair ? 16 : 8);          // a pair takes two horizontally adjacent tiles
+        d.tiles_y = ceil_div(d.in_H, 16 * MT);
+    }
     const long long total = (long long)d.N * d.tiles_y * d.tiles_x * d.n_ntiles * d.nph;
     RRV_REQUIRE(total < (1LL << 31), "rrv_conv2d: too many tiles");
     d.total_tiles = (int)total;
@@ -975,12 +1085,11 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     const int rows = btiles * d.Cout_pad;
     const uint16_t* w_hi = (const uint16_t*)p->w_tc;
     const uint16_t* w_lo = w_hi + (long long)rows * p->Cin;
-    const int box_rows = 16 * MT + 2 * halo;
-    if (encode_act_map(&ma_hi, p->in_hi, d.N, d.in_H, d.in_W, p->Cin, 8, box_rows)) return 1;
-    const int b_box = d.pair ? BN / 2 : BN;
+    if (encode_act_map(&ma_hi, p->in_hi, d.N, d.in_H, d.in_W, p->Cin, box_w, box_rows)) return 1;
+    const int b_box = d.pair ? d.BN / 2 : d.BN;
     if (encode_w_map(&mb_hi, w_hi, rows, p->Cin, b_box)) return 1;
     if (d.x3) {
-        if (encode_act_map(&ma_lo, p->in_lo, d.N, d.in_H, d.in_W, p->Cin, 8, box_rows)) return 1;
+        if (encode_act_map(&ma_lo, p->in_lo, d.N, d.in_H, d.in_W, p->Cin, box_w, box_rows)) return 1;
         if (encode_w_map(&mb_lo, w_lo, rows, p->Cin, b_box)) return 1;
     } else {
         ma_lo = ma_hi;
@@ -1016,6 +1125,11 @@ int tc_tune_pair(int enable, int min_bn) {
     RRV_REQUIRE(min_bn >= 32 && min_bn <= 256 && min_bn % 32 == 0, "rrv_tc_tune_pair: min_bn must be a multiple of 32 in [32, 256]");
     g_tune.pair = enable ? 1 : 0;
     g_tune.pair_min_bn = min_bn;
+    return 0;
+}
+
+int tc_tune_merge(int enable) {
+    g_tune.dym = enable ? 1 : 0;
     return 0;
 }
 

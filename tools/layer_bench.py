@@ -19,6 +19,9 @@ LAYERS = {  # name: (H, W, Cin, Cout, k, ups)
 }
 
 
+FULL = "--full" in sys.argv
+
+
 def bench(name, tunings, iters=5):
     H, W, Cin, Cout, k, ups = LAYERS[name]
     g = torch.Generator().manual_seed(0)
@@ -33,7 +36,15 @@ def bench(name, tunings, iters=5):
     d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = 1, H, W, Cin, Cout, k, ups
     d.in_hi, d.in_lo = L.ptr(xp.hi), L.ptr(xp.lo)
     d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
-    d.ep = make_epilogue(bias=cw.bias, act=1)
+    if FULL and Cout % 8 == 0:      # ResidualBlock.conv2 epilogue: norm1, + half-res shortcut, norm2, AdaIN
+        tab = torch.stack([torch.zeros(Cout), torch.ones(Cout), torch.full((Cout,), -3.0), torch.full((Cout,), 3.0)]).to(dev).contiguous()
+        aff = torch.stack([torch.ones(Cout), torch.zeros(Cout)]).to(dev).contiguous()
+        res = Planes(1, H // 2, W // 2, Cout, True, dev)
+        res.hi.normal_()
+        res.lo.zero_()
+        d.ep = make_epilogue(bias=cw.bias, act=2, norm1=tab, res=res, res_shift=1, norm2=tab, affine=aff)
+    else:
+        d.ep = make_epilogue(bias=cw.bias, act=1)
     if Cout % 8 == 0:
         o = Planes(1, H, W, Cout, True, dev)
         d.out_mode, d.out_hi, d.out_lo = L.OUT_PLANES, L.ptr(o.hi), L.ptr(o.lo)
@@ -42,7 +53,8 @@ def bench(name, tunings, iters=5):
         d.out_mode, d.out_f32, d.out_C = L.OUT_F32_NCHW, o.data_ptr(), 3
     flops = 2.0 * Cin * Cout * k * k * H * W
     res = []
-    for label, (ver, mt, upsv1, pair, minbn, maxbn) in tunings.items():
+    for label, (ver, mt, upsv1, pair, minbn, maxbn, *rest) in tunings.items():
+        L.check(L.lib().rrv_tc_tune_merge(rest[0] if rest else 1))
         L.check(L.lib().rrv_tc_tune2(ver, mt, upsv1))
         L.check(L.lib().rrv_tc_tune_pair(pair, minbn))
         L.check(L.lib().rrv_tc_tune(maxbn, 16, 6))
@@ -60,8 +72,8 @@ def bench(name, tunings, iters=5):
 
 
 if __name__ == "__main__":
-    T = {"default": (2, 2, 0, 1, 128, 256), "pair64": (2, 2, 0, 1, 64, 256), "nopair": (2, 2, 0, 0, 128, 256),
-         "mt1": (2, 1, 0, 1, 128, 256), "bn128": (2, 2, 0, 1, 128, 128), "v1": (1, 2, 1, 0, 128, 256)}
-    names = sys.argv[1:] or list(LAYERS)
+    T = {"default": (2, 2, 0, 1, 64, 256), "nomerge": (2, 2, 0, 1, 64, 256, 0), "nopair": (2, 2, 0, 0, 64, 256),
+         "nopair_nomerge": (2, 2, 0, 0, 64, 256, 0), "v1": (1, 2, 1, 0, 128, 256)}
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(LAYERS)
     for n in names:
         bench(n, T)
