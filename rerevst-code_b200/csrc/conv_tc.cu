@@ -951,14 +951,15 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
 
     const int budget = SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES;
     int a_stage = 0, b_slot = 0, box_w = 8, box_rows = 0;
-    d.dym = (g_tune.dym && p->ksize == 3 && !ups && 3 * d.Cout_pad <= 256 && d.Cout_pad % 32 == 0 && d.in_H >= 8) ? 1 : 0;
+    d.dym = (g_tune.dym && p->ksize == 3 && !ups && 3 * d.Cout_pad <= 256 && d.in_H >= 8) ? 1 : 0;
     if (d.dym) {
         // ---- merged dy taps: N = 3 Cout_pad, M tile = 32 input rows x 4 columns (one TMEM lane quadrant per column) ----
         const int MT = 1;
         d.MT = MT;
         d.BN = 3 * d.Cout_pad; d.BNe = d.Cout_pad; d.b_tile_rows = 3 * d.Cout_pad;
         d.n_ntiles = 1;
-        d.pair = (g_tune.pair && num_sms() % 2 == 0) ? 1 : 0;
+        // (the RGB head, N = 48, stays single-CTA unless pair_min_bn is lowered: each CTA of a pair holds BN / 2 weight rows)
+        d.pair = (g_tune.pair && num_sms() % 2 == 0 && d.BN >= g_tune.pair_min_bn && (d.BN / 2) % 8 == 0) ? 1 : 0;
         a_stage = planes * MT * 16384;
         b_slot = planes * d.BN * 128 / (d.pair ? 2 : 1);
         d.a_plane_bytes = MT * 16384;

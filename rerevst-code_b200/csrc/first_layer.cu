@@ -18,7 +18,8 @@ struct FirstDev {
     int N, H, W, src_kind, gray, lo_fp16;
 };
 
-__device__ __forceinline__ void normalised_rgb(const FirstDev& p, int n, int y, int x, float* v) {
+// Normalised RGB of one pixel as the reference's first convolution would see it WITHOUT RGB2Gray.
+__device__ __forceinline__ void load_normalised(const FirstDev& p, int n, int y, int x, float* v) {
     const float mean[3] = {0.485f, 0.456f, 0.406f};
     const float sd[3] = {0.229f, 0.224f, 0.225f};
     if (p.src_kind == 1) {
@@ -34,13 +35,25 @@ __device__ __forceinline__ void normalised_rgb(const FirstDev& p, int n, int y, 
 #pragma unroll
         for (int c = 0; c < 3; ++c) v[c] = s[(((long long)n * 3 + c) * p.H + y) * p.W + x];
     }
-    if (p.gray) {
-        // RGB2Gray: de-normalise, gray = ch2*0.299 + ch1*0.587 + ch0*0.114, re-normalise per channel
-        float im[3];
+}
+
+// RGB2Gray (:487-497) up to its last step: de-normalise, gray = ch2*0.299 + ch1*0.587 + ch0*0.114 (the BGR weights
+// applied to the RGB tensor, as the reference does).  The re-normalisation per channel follows in the callers.
+__device__ __forceinline__ float gray_value(const float* v) {
+    const float mean[3] = {0.485f, 0.456f, 0.406f};
+    const float sd[3] = {0.229f, 0.224f, 0.225f};
+    float im[3];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) im[c] = __fadd_rn(__fmul_rn(v[c], sd[c]), mean[c]);
-        const float g = __fadd_rn(__fadd_rn(__fmul_rn(im[2], 0.299f), __fmul_rn(im[1], 0.587f)),
-                                  __fmul_rn(im[0], 0.114f));
+    for (int c = 0; c < 3; ++c) im[c] = __fadd_rn(__fmul_rn(v[c], sd[c]), mean[c]);
+    return __fadd_rn(__fadd_rn(__fmul_rn(im[2], 0.299f), __fmul_rn(im[1], 0.587f)), __fmul_rn(im[0], 0.114f));
+}
+
+__device__ __forceinline__ void normalised_rgb(const FirstDev& p, int n, int y, int x, float* v) {
+    const float mean[3] = {0.485f, 0.456f, 0.406f};
+    const float sd[3] = {0.229f, 0.224f, 0.225f};
+    load_normalised(p, n, y, x, v);
+    if (p.gray) {
+        const float g = gray_value(v);
 #pragma unroll
         for (int c = 0; c < 3; ++c) v[c] = __fdiv_rn(__fsub_rn(g, mean[c]), sd[c]);
     }
@@ -126,6 +139,116 @@ __global__ void __launch_bounds__(256) first_layer_kernel(const FirstDev p) {
     }
 }
 
+// Gray frames (every content frame: TransformerNet.forward and .add run RGB2Gray first): the three input
+// channels are affine functions of ONE gray value, v_c = (g - mean_c) / sd_c = a_c u + b_c with the centred
+// variable u = (g - GM) / GS, so the 27-tap convolution collapses to 9 taps on u:
+//     out[co] = bias[co] + sum_{t in bounds} (W1[t][co] u_t + W0[t][co]),
+//     W1[t][co] = sum_c w[co][c][t] a_c,   W0[t][co] = sum_c w[co][c][t] b_c   (|b_c| < 0.25: no cancellation).
+// Zero padding pads v (not g) with zeros: out-of-bounds taps contribute neither term, which the border
+// pixels fix up by subtracting the W0 of their missing taps.  3x fewer FMAs: the kernel becomes store-bound.
+constexpr float GRAY_GM = 0.449f, GRAY_GS = 0.226f;
+
+__global__ void __launch_bounds__(256) first_layer_gray_kernel(const FirstDev p) {
+    constexpr int PH = FL_TH + 2, PW = FL_TW + 2;
+    __shared__ float s_in[PH][PW + 2];
+    __shared__ __align__(16) float s_w1[9][64];
+    __shared__ __align__(16) float s_w0[9][64];
+    __shared__ float s_b[64];
+    const int tid = threadIdx.x;
+    const int tiles_x = (p.W + FL_TW - 1) / FL_TW;
+    const int oy0 = (blockIdx.x / tiles_x) * FL_TH, ox0 = (blockIdx.x % tiles_x) * FL_TW;
+    const int n = blockIdx.y;
+    const float mean[3] = {0.485f, 0.456f, 0.406f};
+    const float sd[3] = {0.229f, 0.224f, 0.225f};
+
+    for (int i = tid; i < 9 * 64; i += 256) {
+        const int co = i & 63, t = i >> 6;
+        float w1 = 0.0f, w0 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float w = p.w[co * 27 + c * 9 + t];
+            w1 = fmaf(w, GRAY_GS / sd[c], w1);
+            w0 = fmaf(w, (GRAY_GM - mean[c]) / sd[c], w0);
+        }
+        s_w1[t][co] = w1;
+        s_w0[t][co] = w0;
+    }
+    for (int i = tid; i < PH * PW; i += 256) {
+        const int r = i / PW, c = i % PW;
+        const int y = oy0 - 1 + r, x = ox0 - 1 + c;
+        float u = 0.0f;
+        if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+            float v[3];
+            load_normalised(p, n, y, x, v);
+            u = (gray_value(v) - GRAY_GM) * (1.0f / GRAY_GS);
+        }
+        s_in[r][c] = u;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float b = p.bias[tid];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) b += s_w0[t][tid];
+        s_b[tid] = b;
+    }
+    __syncthreads();
+
+    // thread = 8 adjacent pixels x 8 output channels: the 8 lanes of a pixel store one full 128-byte line per plane
+    const int q = tid & 7, pg = tid >> 3;
+    const int r = pg >> 2, c0 = (pg & 3) * 8;
+    float acc[8][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[j][k] = s_b[q * 8 + k];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+        float a[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) a[i] = s_in[r + dy][c0 + i];
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const float4* wp = reinterpret_cast<const float4*>(&s_w1[dy * 3 + dx][q * 8]);
+            const float4 wa = wp[0], wb = wp[1];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[j][0] = fmaf(a[j + dx], wa.x, acc[j][0]);
+                acc[j][1] = fmaf(a[j + dx], wa.y, acc[j][1]);
+                acc[j][2] = fmaf(a[j + dx], wa.z, acc[j][2]);
+                acc[j][3] = fmaf(a[j + dx], wa.w, acc[j][3]);
+                acc[j][4] = fmaf(a[j + dx], wb.x, acc[j][4]);
+                acc[j][5] = fmaf(a[j + dx], wb.y, acc[j][5]);
+                acc[j][6] = fmaf(a[j + dx], wb.z, acc[j][6]);
+                acc[j][7] = fmaf(a[j + dx], wb.w, acc[j][7]);
+            }
+        }
+    }
+    const int oy = oy0 + r;
+    if (oy >= p.H) return;
+    const bool edge_row = oy == 0 || oy == p.H - 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int ox = ox0 + c0 + j;
+        if (ox >= p.W) continue;
+        if (edge_row || ox == 0 || ox == p.W - 1) {       // taps that fall outside the image carry no W0 term
+            for (int t = 0; t < 9; ++t) {
+                const int y = oy + t / 3 - 1, x = ox + t % 3 - 1;
+                if (y >= 0 && y < p.H && x >= 0 && x < p.W) continue;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[j][k] -= s_w0[t][q * 8 + k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[j][k] = fmaxf(acc[j][k], 0.0f);
+        const long long o = (((long long)n * p.H + oy) * p.W + ox) * 64 + q * 8;
+        if (p.out_hi != nullptr) store8(p.out_hi + o, p.out_lo ? p.out_lo + o : nullptr, p.lo_fp16, acc[j]);
+        if (p.out_f32 != nullptr) {
+            *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            *reinterpret_cast<float4*>(p.out_f32 + o + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+        }
+    }
+}
+
 int first_layer(const void* src, int src_kind, int gray, int N, int H, int W, const float* w, const float* bias,
                 void* out_hi, void* out_lo, float* out_f32, cudaStream_t st) {
     RRV_REQUIRE(src && w && bias, "rrv_first_layer: NULL input");
@@ -134,6 +257,10 @@ int first_layer(const void* src, int src_kind, int gray, int N, int H, int W, co
     RRV_REQUIRE(out_hi || out_f32, "rrv_first_layer: no output requested");
     FirstDev d{src, w, bias, (uint16_t*)out_hi, (uint16_t*)out_lo, out_f32, N, H, W, src_kind, gray, g_lo_fp16};
     dim3 grid(ceil_div(W, FL_TW) * ceil_div(H, FL_TH), N);
+    if (gray) {
+        first_layer_gray_kernel<<<grid, 256, 0, st>>>(d);
+        return check_launch("first_layer_gray_kernel");
+    }
     first_layer_kernel<<<grid, 256, 0, st>>>(d);
     return check_launch("first_layer_kernel");
 }

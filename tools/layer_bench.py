@@ -73,7 +73,7 @@ def bench(name, tunings, iters=5):
 
 if __name__ == "__main__":
     T = {"default": (2, 2, 0, 1, 64, 256), "nomerge": (2, 2, 0, 1, 64, 256, 0), "nopair": (2, 2, 0, 0, 64, 256),
-         "nopair_nomerge": (2, 2, 0, 0, 64, 256, 0), "v1": (1, 2, 1, 0, 128, 256)}
+         "nopair_nomerge": (2, 2, 0, 0, 64, 256, 0), "v1": (1, 2, 1, 0, 128, 256), "pair32": (2, 2, 0, 1, 32, 256)}
     names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(LAYERS)
     for n in names:
         bench(n, T)
