@@ -82,6 +82,9 @@ typedef struct rrv_conv {
     void* out_lo;           /* NULL: bf16 mode */
     float* out_f32;         /* NHWC [N][H][W][Cout], or NCHW [N][out_C][H][W] */
     int32_t out_C;          /* channels kept for RRV_OUT_F32_NCHW (3 for the RGB head) */
+    int32_t pool;           /* 1: nn.MaxPool2d(2, 2) (vgg19.features[4|9|18], floor) fused behind bias + activation; the
+                             * planes output is [N][H/2][W/2][Cout].  tcgen05 path, ups == 0, Cout % 32 == 0, no norm /
+                             * residual / affine stage. */
 } rrv_conv;
 
 int rrv_conv2d(const rrv_conv* p, int impl, void* stream);

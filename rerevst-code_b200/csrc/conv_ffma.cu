@@ -151,6 +151,7 @@ int conv2d_ffma(const rrv_conv* p, cudaStream_t st) {
     RRV_REQUIRE(p->ksize == 1 || p->ksize == 3, "rrv_conv2d: ksize must be 1 or 3 (got %d)", p->ksize);
     RRV_REQUIRE(p->Cin % CK == 0, "rrv_conv2d: Cin must be a multiple of %d (got %d)", CK, p->Cin);
     RRV_REQUIRE(p->w_f32 != nullptr, "rrv_conv2d(FFMA): w_f32 is NULL");
+    RRV_REQUIRE(!p->pool, "rrv_conv2d(FFMA): the fused max-pool exists on the tcgen05 path only (use rrv_maxpool2x2)");
     RRV_REQUIRE(p->in_hi != nullptr, "rrv_conv2d: in_hi is NULL");
     RRV_REQUIRE(p->N > 0 && p->H > 0 && p->W > 0, "rrv_conv2d: empty output %dx%dx%d", p->N, p->H, p->W);
     RRV_REQUIRE(!p->ups || (p->H % 2 == 0 && p->W % 2 == 0), "rrv_conv2d: ups needs even output size");

@@ -59,7 +59,8 @@ struct TcTune {
 TcTune g_tune;
 
 struct OutDesc {
-    int H, W, Cout, out_mode, out_C;
+    int H, W, Cout, out_mode, out_C;     // H, W: the OUTPUT tensor (half the convolution's size when pool is set)
+    int pool;                            // 2x2/2 max-pool of the epilogue result (vgg19.features[4|9|18]) before the store
     uint16_t* out_hi;
     uint16_t* out_lo;
     float* out_f32;
@@ -334,6 +335,93 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
         chain8<FLAGS>(e, s_tab, ts, c0, r + g * 8, x, rh[g], rl[g], full, px, o.Cout);
         store_group(o, x, px, c0, c0 + 8 <= o.Cout ? 8 : o.Cout - c0);
     }
+}
+
+// Pooled variant (Encoder conv1_2 / conv2_2 / conv3_4, whose only consumer is the 2x2 max-pool): the pool runs on
+// the raw accumulators -- bias + ReLU are monotonic, so they commute with the max -- and only the pooled pixel goes
+// through the chain and to memory (a quarter of the stores; the full-resolution tensor never exists).
+//   !DYM: a warp's 32 lanes are 4 rows x 8 columns of the tile: both partners are lanes (xor 8, xor 1).
+//    DYM: lanes are 32 consecutive rows of ONE column (quadrant = column): the row partner is lane ^ 1, the column
+//         partner lives in the neighbouring warp (warp ^ 1) and is exchanged through `xbuf` (2 KB per warp).
+// `px` is the POOLED pixel (same for the 4 lanes of a 2x2 group, each of which stores one 8-channel group: `sub`).
+template <bool DYM>
+__device__ __forceinline__ void epilogue_chunk_pool(const OutDesc& o, const EpiDev& e, const float* s_tab, int ts, uint32_t taddr,
+                                                    const PixCtx& px, int cb, int sub, float* xbuf, int warp, int lane) {
+    uint32_t r[CW];
+    ptx::tmem_ld32_issue(taddr, r);
+    if (DYM) {
+        uint32_t r1[CW], r2[CW];
+        ptx::tmem_ld32_issue(taddr + (uint32_t)ts, r1);
+        ptx::tmem_ld32_issue(taddr + (uint32_t)(2 * ts), r2);
+        ptx::tmem_ld32_wait(r);
+        ptx::tmem_ld32_wait(r1);
+        ptx::tmem_ld32_wait(r2);
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+            const float a = __uint_as_float(r[i]);
+            const float b = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[i]), 1);
+            const float c = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[i]), 2);
+            const float v = (a + b) + c;
+            r[i] = __float_as_uint(fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1)));       // row partner
+        }
+        // publish one 16-channel half per lane (both lanes of a row pair hold the same maxima)
+        const int h = lane & 1;
+        float4* wb = reinterpret_cast<float4*>(xbuf + (warp - 2) * 512 + lane * 16);
+        const int sw = (lane >> 1) & 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float4 v;
+            v.x = __uint_as_float(h ? r[16 + 4 * j + 0] : r[4 * j + 0]);
+            v.y = __uint_as_float(h ? r[16 + 4 * j + 1] : r[4 * j + 1]);
+            v.z = __uint_as_float(h ? r[16 + 4 * j + 2] : r[4 * j + 2]);
+            v.w = __uint_as_float(h ? r[16 + 4 * j + 3] : r[4 * j + 3]);
+            wb[j ^ sw] = v;
+        }
+        const int bar_id = 1 + ((warp - 2) >> 1);
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+    } else {
+        ptx::tmem_ld32_wait(r);
+#pragma unroll
+        for (int i = 0; i < CW; ++i) {
+            float v = __uint_as_float(r[i]);
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+            v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
+            r[i] = __float_as_uint(v);
+        }
+    }
+    // this lane's 8-channel group
+    uint32_t sel[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t lo2 = (sub & 1) ? r[8 + k] : r[k];
+        const uint32_t hi2 = (sub & 1) ? r[24 + k] : r[16 + k];
+        sel[k] = (sub & 2) ? hi2 : lo2;
+    }
+    if (DYM) {
+        // the column partner's maxima of the same group: written by its lane 2 (lane >> 1) + (sub >> 1), float4 (sub & 1) 2 + {0, 1}
+        const int wl = ((lane >> 1) << 1) + (sub >> 1);
+        const float4* rb = reinterpret_cast<const float4*>(xbuf + ((warp - 2) ^ 1) * 512 + wl * 16);
+        const int sw = (wl >> 1) & 3, j0 = (sub & 1) * 2;
+        const float4 p0 = rb[j0 ^ sw], p1 = rb[(j0 + 1) ^ sw];
+        sel[0] = __float_as_uint(fmaxf(__uint_as_float(sel[0]), p0.x));
+        sel[1] = __float_as_uint(fmaxf(__uint_as_float(sel[1]), p0.y));
+        sel[2] = __float_as_uint(fmaxf(__uint_as_float(sel[2]), p0.z));
+        sel[3] = __float_as_uint(fmaxf(__uint_as_float(sel[3]), p0.w));
+        sel[4] = __float_as_uint(fmaxf(__uint_as_float(sel[4]), p1.x));
+        sel[5] = __float_as_uint(fmaxf(__uint_as_float(sel[5]), p1.y));
+        sel[6] = __float_as_uint(fmaxf(__uint_as_float(sel[6]), p1.z));
+        sel[7] = __float_as_uint(fmaxf(__uint_as_float(sel[7]), p1.w));
+        const int bar_id = 1 + ((warp - 2) >> 1);
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");       // the buffers may be rewritten
+    }
+    if (!px.valid) return;
+    float x[8];
+    const uint4 none = make_uint4(0, 0, 0, 0);
+    chain8<0>(e, s_tab, ts, cb + sub * 8, sel, x, none, none, true, px, o.Cout);
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    *reinterpret_cast<uint4*>(o.out_hi + px.out_off + cb + sub * 8) = hi;
+    if (o.out_lo) *reinterpret_cast<uint4*>(o.out_lo + px.out_off + cb + sub * 8) = lo;
 }
 
 template <int FLAGS>
@@ -736,11 +824,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const uint32_t t_set = tmem_base + (uint32_t)(as * p.set_stride) + ((uint32_t)(quad * 32) << 16);
             for (int mt = 0; mt < p.MT; ++mt) {
                 const int iy = y0 + (p.dym ? 0 : 16 * mt) + ty, ix = x0 + (p.dym ? 4 * mt : 0) + tx;
+                const uint32_t ta = t_set + (uint32_t)(mt * p.acc_stride);
+                if (FLAGS == 0 && p.o.pool) {
+                    // fused 2x2 max-pool: the pooled pixel (iy >> 1, ix >> 1); an odd last row / column is dropped (floor)
+                    const bool pvalid = (iy >> 1) < p.o.H && (ix >> 1) < p.o.W && (!p.dym || ty < 30);
+                    const PixCtx px = make_pix(p.o, e, n, iy >> 1, ix >> 1, pvalid);
+                    float* xbuf = s_tab + (TAB_BYTES / 4) * p.Cout_pad;      // after the constants table (merged-tap layers only)
+                    for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4) {
+                        if (p.dym) epilogue_chunk_pool<true>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW,
+                                                             (lane & 1) | ((quad & 1) << 1), xbuf, warp, lane);
+                        else epilogue_chunk_pool<false>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW,
+                                                        (lane & 1) | (((lane >> 3) & 1) << 1), xbuf, warp, lane);
+                    }
+                    continue;
+                }
                 const bool valid = iy < p.in_H && ix < p.in_W && (!p.dym || ty < 30);
                 const int oy = p.nph == 4 ? 2 * iy + (ph >> 1) : iy;
                 const int ox = p.nph == 4 ? 2 * ix + (ph & 1) : ix;
                 const PixCtx px = make_pix(p.o, e, n, oy, ox, valid);
-                const uint32_t ta = t_set + (uint32_t)(mt * p.acc_stride);
                 for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4) {
                     if (p.dym) epilogue_chunk<FLAGS, true>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, ch * CW, p.BNe);
                     else epilogue_chunk<FLAGS, false>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, ch * CW, p.BNe);
@@ -855,7 +956,8 @@ int cout_pad_of(int Cout) { return (Cout + 15) / 16 * 16; }
 
 OutDesc make_out(const rrv_conv* p) {
     OutDesc o;
-    o.H = p->H; o.W = p->W; o.Cout = p->Cout; o.out_mode = p->out_mode; o.out_C = p->out_C;
+    o.pool = p->pool ? 1 : 0;
+    o.H = p->H >> o.pool; o.W = p->W >> o.pool; o.Cout = p->Cout; o.out_mode = p->out_mode; o.out_C = p->out_C;
     o.out_hi = (uint16_t*)p->out_hi; o.out_lo = (uint16_t*)p->out_lo; o.out_f32 = p->out_f32;
     return o;
 }
@@ -949,9 +1051,10 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     const int btiles = ups ? 16 : p->ksize * p->ksize;     // weight tiles per chunk in the blob
     const int btiles_tile = ups ? 4 : btiles;               // ... of which one tile (= one phase) uses this many
 
-    const int budget = SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES;
     int a_stage = 0, b_slot = 0, box_w = 8, box_rows = 0;
     d.dym = (g_tune.dym && p->ksize == 3 && !ups && 3 * d.Cout_pad <= 256 && d.in_H >= 8) ? 1 : 0;
+    const int xchg_bytes = (p->pool && d.dym) ? EPI_WARPS * 2048 : 0;      // column-partner exchange of the fused max-pool
+    const int budget = SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES - xchg_bytes;
     if (d.dym) {
         // ---- merged dy taps: N = 3 Cout_pad, M tile = 32 input rows x 4 columns (one TMEM lane quadrant per column) ----
         const int MT = 1;
@@ -1096,7 +1199,7 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         ma_lo = ma_hi;
         mb_lo = mb_hi;
     }
-    const int smem = d.a_stages * a_stage + d.b_slots * b_slot + d.Cout_pad * TAB_BYTES + 1024;
+    const int smem = d.a_stages * a_stage + d.b_slots * b_slot + d.Cout_pad * TAB_BYTES + xchg_bytes + 1024;
     const int flags = epi_flags(p->ep);
     const int grid = d.pair ? 2 * std::min(d.total_tiles, num_sms() / 2) : std::min(d.total_tiles, num_sms());
     switch (flags) {
@@ -1183,6 +1286,12 @@ int conv2d_tc(const rrv_conv* p, cudaStream_t st) {
         RRV_REQUIRE(p->out_mode != RRV_OUT_F32_NCHW || p->out_C > 0, "rrv_conv2d: out_C must be set for NCHW output");
     }
 
+    if (p->pool) {
+        RRV_REQUIRE(!ups && p->out_mode == RRV_OUT_PLANES && p->Cout % 32 == 0 && g_tune.version == 2,
+                    "rrv_conv2d(pool): needs a plain (not upsampling) convolution, planes output, Cout %% 32 == 0 and the v2 main loop");
+        RRV_REQUIRE(epi_flags(p->ep) == 0, "rrv_conv2d(pool): only bias + activation may precede the fused max-pool");
+        RRV_REQUIRE(p->H >= 2 && p->W >= 2, "rrv_conv2d(pool): empty pooled output");
+    }
     if (g_tune.version == 2 && !(ups && g_tune.ups_v1)) return conv2d_tc2(p, st);
 
     TcParams d;

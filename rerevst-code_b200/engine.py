@@ -167,9 +167,11 @@ class StyleEngine:
                 self._fold_filter(f, a, b)
 
     # ------------------------------------------------------------------ thin wrappers over the C ABI
-    def _conv(self, cw, x, ep, out_mode=L.OUT_PLANES, out=None, N=None, out_C=0):
+    def _conv(self, cw, x, ep, out_mode=L.OUT_PLANES, out=None, N=None, out_C=0, pool=False):
         N = x.N if N is None else N
         H, W = (x.H * 2, x.W * 2) if cw.ups else (x.H, x.W)
+        if pool and (self._impl_for(cw) != L.IMPL_TCGEN05 or cw.Cout % 32 != 0 or H < 2 or W < 2):
+            return self._pool(self._conv(cw, x, ep, out_mode, None, N, out_C))       # FFMA bring-up path: separate pool kernel
         assert x.C == cw.Cin, (x.C, cw.Cin)
         d = L.Conv()
         d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = N, H, W, cw.Cin, cw.Cout, cw.ksize, int(cw.ups)
@@ -177,8 +179,9 @@ class StyleEngine:
         d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
         d.ep = ep
         d.out_mode = out_mode
+        d.pool = int(pool)
         if out_mode == L.OUT_PLANES:
-            out = out or Planes(N, H, W, cw.Cout, self.x3, self.device)
+            out = out or Planes(N, H >> int(pool), W >> int(pool), cw.Cout, self.x3, self.device)
             d.out_hi, d.out_lo = L.ptr(out.hi), L.ptr(out.lo)
         elif out_mode == L.OUT_F32_NHWC:
             out = out if out is not None else torch.empty((N, H, W, cw.Cout), dtype=torch.float32, device=self.device)
@@ -267,9 +270,7 @@ class StyleEngine:
             elif last:
                 return self._conv(cw, x, make_epilogue(bias=cw.bias, act=1, norm1=norm0))
             else:
-                x = self._conv(cw, x, ep)
-            if idx in VGG_POOL_AFTER:
-                x = self._pool(x)
+                x = self._conv(cw, x, ep, pool=idx in VGG_POOL_AFTER)     # MaxPool2d fused into the epilogue
         return taps
 
     # ------------------------------------------------------------------ style (once per style image)

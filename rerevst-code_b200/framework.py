@@ -36,9 +36,13 @@ class Stylization:
             raise ValueError("expected a uint8 HxWx3 BGR image (cv2.imread layout)")
         key = img.shape
         if key not in self._pin:
-            self._pin[key] = torch.empty((1,) + key, dtype=torch.uint8).pin_memory()
-        self._pin[key][0].copy_(torch.from_numpy(img))
-        return self._pin[key].to(self.device, non_blocking=True)
+            self._pin[key] = (torch.empty((1,) + key, dtype=torch.uint8).pin_memory(), torch.cuda.Event())
+        pinned, copied = self._pin[key]
+        copied.synchronize()                    # the previous asynchronous upload from this staging buffer has finished
+        pinned[0].copy_(torch.from_numpy(img))
+        dev = pinned.to(self.device, non_blocking=True)
+        copied.record(torch.cuda.current_stream(self.device))
+        return dev
 
     # ===== Sequence-Level Global Feature Sharing =====
     def add(self, patch):

@@ -477,6 +477,45 @@ def test_conv_main_loop_variants(L, dev, tune):
         L.check(L.lib().rrv_tc_tune_pair(1, 64))
 
 
+@pytest.mark.parametrize("case", [(1, 64, 40, 64, 64), (2, 37, 21, 64, 64), (1, 32, 48, 128, 128), (2, 19, 27, 128, 128),
+                                  (1, 24, 16, 256, 256), (1, 60, 8, 64, 96)])
+@pytest.mark.parametrize("pair,merge", [(1, 1), (0, 1), (1, 0)])
+def test_conv_fused_maxpool(L, dev, case, pair, merge):
+    """rrv_conv.pool: nn.MaxPool2d(2, 2) of vgg19.features[4|9|18] in the epilogue of the convolution before it
+    (merged-tap layout: column partner exchanged between warps; plain layout: both partners in the warp).
+    Must equal the separate pool kernel applied to the unpooled kernel output bit for bit (odd sizes floor)."""
+    from rerevst_code_b200.engine import ConvW, Planes, make_epilogue
+    N, H, W, Cin, Cout = case
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    cw = ConvW(w.to(dev), b.to(dev))
+    xp = _to_planes(L, x.to(dev))
+    L.check(L.lib().rrv_tc_tune_pair(pair, 64))
+    L.check(L.lib().rrv_tc_tune_merge(merge))
+    try:
+        outs = []
+        for pool in (0, 1):
+            d = L.Conv()
+            d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = N, H, W, Cin, Cout, 3, 0
+            d.in_hi, d.in_lo = L.ptr(xp.hi), L.ptr(xp.lo)
+            d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
+            d.ep = make_epilogue(bias=cw.bias, act=1)
+            d.pool = pool
+            o = Planes(N, H >> pool, W >> pool, Cout, True, dev)
+            o.hi.fill_(float("nan"))
+            d.out_mode, d.out_hi, d.out_lo = L.OUT_PLANES, L.ptr(o.hi), L.ptr(o.lo)
+            L.check(L.lib().rrv_conv2d(C.byref(d), L.IMPL_TCGEN05, L.stream()), str(case))
+            outs.append(_from_planes(L, o).cpu())
+        ref = F.relu(F.conv2d(_from_planes(L, xp).cpu(), w, b, padding=1))
+        assert rel_linf(outs[0], ref) < 2e-4
+        assert torch.equal(outs[1], F.max_pool2d(outs[0], 2, 2)), (case, pair, merge)
+    finally:
+        L.check(L.lib().rrv_tc_tune_pair(1, 64))
+        L.check(L.lib().rrv_tc_tune_merge(1))
+
+
 def test_transfer_stream_equals_transfer(L, dev, state_dict):
     from rerevst_code_b200.framework import Stylization
     rng = np.random.RandomState(5)
