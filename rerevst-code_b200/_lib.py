@@ -10,7 +10,7 @@ import os
 import torch  # noqa: F401  (loads libcudart.so.12 into the process before our library)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "librerevst_b200.so")
+LIB_PATH = os.environ.get("RRV_LIB_PATH") or os.path.join(_HERE, "csrc", "librerevst_b200.so")   # override: kernel experiments
 
 OUT_PLANES, OUT_F32_NHWC, OUT_F32_NCHW = 0, 1, 2
 IMPL_FFMA, IMPL_TCGEN05 = 0, 1

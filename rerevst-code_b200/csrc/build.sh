@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC"
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC ${RRV_DEFS}"
 mkdir -p build
 pids=()
 for f in capi conv_ffma conv_tc first_layer pointwise stats warp; do

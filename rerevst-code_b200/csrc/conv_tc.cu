@@ -31,6 +31,16 @@
 #include "rrv_common.cuh"
 #include "tc_ptx.cuh"
 
+#ifndef RRV_EPI_PREFETCH
+#define RRV_EPI_PREFETCH 2      // before waiting for the accumulators: 1 = load the first chunk's residual into registers
+#endif                          // (spills at 168 registers), 2 = prefetch its cache lines into L1 (no registers)
+#ifndef RRV_EPI_HALF16
+#define RRV_EPI_HALF16 1        // merged-tap epilogue: combine the three taps 16 columns at a time (register pressure)
+#endif
+#ifndef RRV_EPI_FOLD
+#define RRV_EPI_FOLD 1          // norm stages as one FMA + clamps with pre-multiplied constants
+#endif
+
 namespace rrv {
 
 namespace {
@@ -52,7 +62,7 @@ struct TcTune {
     int version = 2;        // main loop: 1 = one box per tap, 2 = row-reuse / shared weight tiles
     int mt = 2;             // v2: M tiles (128 pixels each) per weight tile
     int ups_v1 = 0;         // 1: nearest-x2 convolutions use the v1 main loop
-    int dym = 1;            // v2: merge the three dy taps along N when 3 Cout_pad <= 256 (the 64-channel layers)
+    int dxm = 1;            // v2: merge the three dx taps along N when 3 Cout_pad <= 256 (the 64-channel layers, the RGB head)
     int pair = 1;           // v2: CTA pairs (cta_group::2) for Cout tiles >= pair_min_bn
     int pair_min_bn = 64;   // (<= 64 also overrides resident weights: measured faster on the 64 -> 64 layers)
 };
@@ -125,17 +135,38 @@ __device__ __forceinline__ void fill_epilogue_table(float* s_tab, const EpiDev& 
     for (int ch = threadIdx.x; ch < Cout_pad; ch += nthreads) {
         const bool in = ch < Cout;
         const int C = Cout;
+        const float m1 = (in && e.norm1) ? e.norm1[ch] : 0.0f, r1 = (in && e.norm1) ? e.norm1[C + ch] : 1.0f;
+        const float lo1 = (in && e.norm1) ? e.norm1[2 * C + ch] : -CUDART_INF_F, hi1 = (in && e.norm1) ? e.norm1[3 * C + ch] : CUDART_INF_F;
+        const float m2 = (in && e.norm2) ? e.norm2[ch] : 0.0f, r2 = (in && e.norm2) ? e.norm2[C + ch] : 1.0f;
+        const float lo2 = (in && e.norm2) ? e.norm2[2 * C + ch] : -CUDART_INF_F, hi2 = (in && e.norm2) ? e.norm2[3 * C + ch] : CUDART_INF_F;
+        const float sc = (in && e.affine) ? e.affine[ch] : 1.0f, sh = (in && e.affine) ? e.affine[C + ch] : 0.0f;
         s_tab[T_BIAS * Cout_pad + ch] = (in && e.bias) ? e.bias[ch] : 0.0f;
-        s_tab[T_M1 * Cout_pad + ch] = (in && e.norm1) ? e.norm1[ch] : 0.0f;
-        s_tab[T_R1 * Cout_pad + ch] = (in && e.norm1) ? e.norm1[C + ch] : 1.0f;
-        s_tab[T_LO1 * Cout_pad + ch] = (in && e.norm1) ? e.norm1[2 * C + ch] : -CUDART_INF_F;
-        s_tab[T_HI1 * Cout_pad + ch] = (in && e.norm1) ? e.norm1[3 * C + ch] : CUDART_INF_F;
-        s_tab[T_M2 * Cout_pad + ch] = (in && e.norm2) ? e.norm2[ch] : 0.0f;
-        s_tab[T_R2 * Cout_pad + ch] = (in && e.norm2) ? e.norm2[C + ch] : 1.0f;
-        s_tab[T_LO2 * Cout_pad + ch] = (in && e.norm2) ? e.norm2[2 * C + ch] : -CUDART_INF_F;
-        s_tab[T_HI2 * Cout_pad + ch] = (in && e.norm2) ? e.norm2[3 * C + ch] : CUDART_INF_F;
-        s_tab[T_SCALE * Cout_pad + ch] = (in && e.affine) ? e.affine[ch] : 1.0f;
-        s_tab[T_SHIFT * Cout_pad + ch] = (in && e.affine) ? e.affine[C + ch] : 0.0f;
+#if RRV_EPI_FOLD
+        // (x - m) r            ->  fma(x, r, -m r)
+        // ((x - m) r) s + t    ->  fma(x, r s, t - m r s), the clamp bounds mapped through the same affine (s = a std > 0)
+        s_tab[T_M1 * Cout_pad + ch] = -m1 * r1;
+        s_tab[T_R1 * Cout_pad + ch] = r1;
+        s_tab[T_LO1 * Cout_pad + ch] = lo1;
+        s_tab[T_HI1 * Cout_pad + ch] = hi1;
+        // a negative scale (never produced by cal_mean_std, std > 0) swaps the bounds; a zero scale makes the output the shift
+        s_tab[T_M2 * Cout_pad + ch] = fmaf(-m2 * r2, sc, sh);
+        s_tab[T_R2 * Cout_pad + ch] = r2 * sc;
+        s_tab[T_LO2 * Cout_pad + ch] = sc == 0.0f ? -CUDART_INF_F : fmaf(sc > 0.0f ? lo2 : hi2, sc, sh);
+        s_tab[T_HI2 * Cout_pad + ch] = sc == 0.0f ? CUDART_INF_F : fmaf(sc > 0.0f ? hi2 : lo2, sc, sh);
+        s_tab[T_SCALE * Cout_pad + ch] = 1.0f;
+        s_tab[T_SHIFT * Cout_pad + ch] = 0.0f;
+#else
+        s_tab[T_M1 * Cout_pad + ch] = m1;
+        s_tab[T_R1 * Cout_pad + ch] = r1;
+        s_tab[T_LO1 * Cout_pad + ch] = lo1;
+        s_tab[T_HI1 * Cout_pad + ch] = hi1;
+        s_tab[T_M2 * Cout_pad + ch] = m2;
+        s_tab[T_R2 * Cout_pad + ch] = r2;
+        s_tab[T_LO2 * Cout_pad + ch] = lo2;
+        s_tab[T_HI2 * Cout_pad + ch] = hi2;
+        s_tab[T_SCALE * Cout_pad + ch] = sc;
+        s_tab[T_SHIFT * Cout_pad + ch] = sh;
+#endif
     }
 }
 
@@ -219,13 +250,13 @@ __device__ __forceinline__ void chain8(const EpiDev& e, const float* s_tab, int 
         for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.0f);
     } else if (e.act == 2) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = x[i] > 0.0f ? x[i] : 0.2f * x[i];
+        for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.2f * x[i]);          // LeakyReLU(0.2): the slope is < 1
     }
     if (has_n1) {
         lds8(s_tab + T_M1 * ts + c0, k0);
         lds8(s_tab + T_R1 * ts + c0, k1);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = (x[i] - k0[i]) * k1[i];
+        for (int i = 0; i < 8; ++i) x[i] = RRV_EPI_FOLD ? fmaf(x[i], k1[i], k0[i]) : (x[i] - k0[i]) * k1[i];
         lds8(s_tab + T_LO1 * ts + c0, k0);
         lds8(s_tab + T_HI1 * ts + c0, k1);
 #pragma unroll
@@ -255,6 +286,20 @@ __device__ __forceinline__ void chain8(const EpiDev& e, const float* s_tab, int 
             }
         }
     }
+#if RRV_EPI_FOLD
+    if (has_n2 || has_aff) {              // Decoder.norm[i] and AdaIN as one FMA; the clamp bounds went through the same affine
+        lds8(s_tab + T_M2 * ts + c0, k0);
+        lds8(s_tab + T_R2 * ts + c0, k1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fmaf(x[i], k1[i], k0[i]);
+        if (has_n2) {
+            lds8(s_tab + T_LO2 * ts + c0, k0);
+            lds8(s_tab + T_HI2 * ts + c0, k1);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = fminf(k1[i], fmaxf(k0[i], x[i]));
+        }
+    }
+#else
     if (has_n2) {
         lds8(s_tab + T_M2 * ts + c0, k0);
         lds8(s_tab + T_R2 * ts + c0, k1);
@@ -271,21 +316,43 @@ __device__ __forceinline__ void chain8(const EpiDev& e, const float* s_tab, int 
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = x[i] * k0[i] + k1[i];
     }
+#endif
 }
 
 // One CW-channel chunk of one accumulator row (= one output pixel): tcgen05.ld, the fused chain, the stores.
 // cb = first global output channel of the chunk, col0 = its first column inside the Cout tile.
 // FLAGS >= 0 fixes the set of stages at compile time (EPI_* bits); FLAGS < 0 reads it from `e`.
-// DYM: the accumulator holds the three dy taps side by side (columns [0,Cp) [Cp,2Cp) [2Cp,3Cp), Cp = ts) for INPUT
-// row = lane; output row `lane` = tap0[lane] + tap1[lane+1] + tap2[lane+2] (the lanes of one quadrant are
-// consecutive rows of one image column).
-template <int FLAGS, bool DYM>
+// DXM: the accumulator holds the three dx taps side by side (columns [0,Cp) [Cp,2Cp) [2Cp,3Cp), Cp = ts) for INPUT
+// column = lane; output column `lane` = tap0[lane] + tap1[lane+1] + tap2[lane+2] (the lanes of one quadrant are
+// 32 consecutive columns of one image row, the first of them one left of the tile).
+template <int FLAGS, bool DXM>
 __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e, const float* s_tab, int ts, uint32_t taddr,
-                                               const PixCtx& px, int cb, int col0, int BN) {
+                                               const PixCtx& px, int cb, int col0, int BN, bool pre = false,
+                                               const uint4* pre_rh = nullptr, const uint4* pre_rl = nullptr) {
     const bool has_res = FLAGS >= 0 ? (FLAGS & EPI_RES) != 0 : e.res_hi != nullptr;
     uint32_t r[CW];
-    ptx::tmem_ld32_issue(taddr, r);
-    if (DYM) {
+    if (DXM && RRV_EPI_HALF16) {
+#pragma unroll
+        for (int h = 0; h < CW / 16; ++h) {
+            uint32_t a0[16], a1[16], a2[16];
+            ptx::tmem_ld16_issue(taddr + (uint32_t)(16 * h), a0);
+            ptx::tmem_ld16_issue(taddr + (uint32_t)(ts + 16 * h), a1);
+            ptx::tmem_ld16_issue(taddr + (uint32_t)(2 * ts + 16 * h), a2);
+            ptx::tmem_ld16_wait(a0);
+            ptx::tmem_ld16_wait(a1);
+            ptx::tmem_ld16_wait(a2);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float a = __uint_as_float(a0[i]);
+                const float b = __shfl_down_sync(0xffffffffu, __uint_as_float(a1[i]), 1);
+                const float c = __shfl_down_sync(0xffffffffu, __uint_as_float(a2[i]), 2);
+                r[16 * h + i] = __float_as_uint((a + b) + c);
+            }
+        }
+    } else {
+        ptx::tmem_ld32_issue(taddr, r);
+    }
+    if (DXM && !RRV_EPI_HALF16) {
         uint32_t r1[CW], r2[CW];
         ptx::tmem_ld32_issue(taddr + (uint32_t)ts, r1);
         ptx::tmem_ld32_issue(taddr + (uint32_t)(2 * ts), r2);
@@ -303,14 +370,20 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
     // the residual of the whole chunk goes in flight while the TMEM load completes
     uint4 rh[CW / 8], rl[CW / 8];
     const bool full = cb + CW <= o.Cout && col0 + CW <= BN;        // warp-uniform
-    if (has_res && px.valid && full) {
+    if (pre) {                                                     // loaded by the caller while the MMAs were still running
+#pragma unroll
+        for (int g = 0; g < CW / 8; ++g) {
+            rh[g] = pre_rh[g];
+            rl[g] = pre_rl[g];
+        }
+    } else if (has_res && px.valid && full) {
 #pragma unroll
         for (int g = 0; g < CW / 8; ++g) {
             rh[g] = *reinterpret_cast<const uint4*>(e.res_hi + px.res_off + cb + g * 8);
             if (e.res_lo) rl[g] = *reinterpret_cast<const uint4*>(e.res_lo + px.res_off + cb + g * 8);
         }
     }
-    if (!DYM) ptx::tmem_ld32_wait(r);
+    if (!DXM) ptx::tmem_ld32_wait(r);
     if (!px.valid) return;
     if (full && o.out_mode == RRV_OUT_PLANES) {
         // fast path (every per-frame layer but the RGB head): no per-group range checks, planes output
@@ -340,16 +413,16 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
 // Pooled variant (Encoder conv1_2 / conv2_2 / conv3_4, whose only consumer is the 2x2 max-pool): the pool runs on
 // the raw accumulators -- bias + ReLU are monotonic, so they commute with the max -- and only the pooled pixel goes
 // through the chain and to memory (a quarter of the stores; the full-resolution tensor never exists).
-//   !DYM: a warp's 32 lanes are 4 rows x 8 columns of the tile: both partners are lanes (xor 8, xor 1).
-//    DYM: lanes are 32 consecutive rows of ONE column (quadrant = column): the row partner is lane ^ 1, the column
-//         partner lives in the neighbouring warp (warp ^ 1) and is exchanged through `xbuf` (2 KB per warp).
+//   !DXM: a warp's 32 lanes are 4 rows x 8 columns of the tile: both partners are lanes (xor 8, xor 1).
+//    DXM: lanes are 32 consecutive columns of ONE row (quadrant = row): the column partner is lane ^ 1, the row
+//         partner lives in the neighbouring warp (warp ^ 1) and is exchanged through `xbuf` (512 B per warp).
 // `px` is the POOLED pixel (same for the 4 lanes of a 2x2 group, each of which stores one 8-channel group: `sub`).
-template <bool DYM>
+template <bool DXM>
 __device__ __forceinline__ void epilogue_chunk_pool(const OutDesc& o, const EpiDev& e, const float* s_tab, int ts, uint32_t taddr,
                                                     const PixCtx& px, int cb, int sub, float* xbuf, int warp, int lane) {
     uint32_t r[CW];
     ptx::tmem_ld32_issue(taddr, r);
-    if (DYM) {
+    if (DXM) {
         uint32_t r1[CW], r2[CW];
         ptx::tmem_ld32_issue(taddr + (uint32_t)ts, r1);
         ptx::tmem_ld32_issue(taddr + (uint32_t)(2 * ts), r2);
@@ -362,23 +435,8 @@ __device__ __forceinline__ void epilogue_chunk_pool(const OutDesc& o, const EpiD
             const float b = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[i]), 1);
             const float c = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[i]), 2);
             const float v = (a + b) + c;
-            r[i] = __float_as_uint(fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1)));       // row partner
+            r[i] = __float_as_uint(fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1)));       // column partner
         }
-        // publish one 16-channel half per lane (both lanes of a row pair hold the same maxima)
-        const int h = lane & 1;
-        float4* wb = reinterpret_cast<float4*>(xbuf + (warp - 2) * 512 + lane * 16);
-        const int sw = (lane >> 1) & 3;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float4 v;
-            v.x = __uint_as_float(h ? r[16 + 4 * j + 0] : r[4 * j + 0]);
-            v.y = __uint_as_float(h ? r[16 + 4 * j + 1] : r[4 * j + 1]);
-            v.z = __uint_as_float(h ? r[16 + 4 * j + 2] : r[4 * j + 2]);
-            v.w = __uint_as_float(h ? r[16 + 4 * j + 3] : r[4 * j + 3]);
-            wb[j ^ sw] = v;
-        }
-        const int bar_id = 1 + ((warp - 2) >> 1);
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
     } else {
         ptx::tmem_ld32_wait(r);
 #pragma unroll
@@ -397,22 +455,31 @@ __device__ __forceinline__ void epilogue_chunk_pool(const OutDesc& o, const EpiD
         const uint32_t hi2 = (sub & 1) ? r[24 + k] : r[16 + k];
         sel[k] = (sub & 2) ? hi2 : lo2;
     }
-    if (DYM) {
-        // the column partner's maxima of the same group: written by its lane 2 (lane >> 1) + (sub >> 1), float4 (sub & 1) 2 + {0, 1}
-        const int wl = ((lane >> 1) << 1) + (sub >> 1);
-        const float4* rb = reinterpret_cast<const float4*>(xbuf + ((warp - 2) ^ 1) * 512 + wl * 16);
-        const int sw = (wl >> 1) & 3, j0 = (sub & 1) * 2;
-        const float4 p0 = rb[j0 ^ sw], p1 = rb[(j0 + 1) ^ sw];
-        sel[0] = __float_as_uint(fmaxf(__uint_as_float(sel[0]), p0.x));
-        sel[1] = __float_as_uint(fmaxf(__uint_as_float(sel[1]), p0.y));
-        sel[2] = __float_as_uint(fmaxf(__uint_as_float(sel[2]), p0.z));
-        sel[3] = __float_as_uint(fmaxf(__uint_as_float(sel[3]), p0.w));
-        sel[4] = __float_as_uint(fmaxf(__uint_as_float(sel[4]), p1.x));
-        sel[5] = __float_as_uint(fmaxf(__uint_as_float(sel[5]), p1.y));
-        sel[6] = __float_as_uint(fmaxf(__uint_as_float(sel[6]), p1.z));
-        sel[7] = __float_as_uint(fmaxf(__uint_as_float(sel[7]), p1.w));
+    if (DXM) {
+        // The row partner (warp ^ 1) stores the groups with the other quadrant parity: publish that group of this lane
+        // pair (`sub ^ 2`) and take the partner's copy of this lane's own group, 4 channels per round (512 B per warp).
+        uint32_t pub[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t lo2 = (sub & 1) ? r[8 + k] : r[k];
+            const uint32_t hi2 = (sub & 1) ? r[24 + k] : r[16 + k];
+            pub[k] = (sub & 2) ? lo2 : hi2;
+        }
+        float4* mine = reinterpret_cast<float4*>(xbuf) + (warp - 2) * 32 + lane;
+        const float4* theirs = reinterpret_cast<const float4*>(xbuf) + ((warp - 2) ^ 1) * 32 + lane;
         const int bar_id = 1 + ((warp - 2) >> 1);
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");       // the buffers may be rewritten
+#pragma unroll
+        for (int rd = 0; rd < 2; ++rd) {
+            *mine = make_float4(__uint_as_float(pub[4 * rd]), __uint_as_float(pub[4 * rd + 1]), __uint_as_float(pub[4 * rd + 2]),
+                                __uint_as_float(pub[4 * rd + 3]));
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            const float4 q = *theirs;
+            sel[4 * rd + 0] = __float_as_uint(fmaxf(__uint_as_float(sel[4 * rd + 0]), q.x));
+            sel[4 * rd + 1] = __float_as_uint(fmaxf(__uint_as_float(sel[4 * rd + 1]), q.y));
+            sel[4 * rd + 2] = __float_as_uint(fmaxf(__uint_as_float(sel[4 * rd + 2]), q.z));
+            sel[4 * rd + 3] = __float_as_uint(fmaxf(__uint_as_float(sel[4 * rd + 3]), q.w));
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");       // the slot may be rewritten
+        }
     }
     if (!px.valid) return;
     float x[8];
@@ -482,7 +549,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 for (int t = 0; t < p.ntaps; ++t) {
                     int oy, ox;
                     tap_offset(p, c, t, oy, ox);
-                    const int tb = (p.nphase == 1 && p.ksize == 3) ? (t % 3) * 3 + t / 3 : t;     // blob order is dx-major for 3x3
+                    const int tb = t;                                    // blob order = PyTorch tap order (dy * 3 + dx)
                     const int brow = (c.phase * p.ntaps + tb) * p.Cout_pad + c.n0;
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         ptx::mbar_wait(ptx::smem_u32(&s_empty[stage]), phase ^ 1u);
@@ -600,7 +667,7 @@ struct Tc2Params {
     int BN, x3;             // BN = N of the MMA (3 Cout_pad when the dy taps are merged)
     int BNe;                // output channels per tile (= BN, or Cout_pad when merged)
     int b_tile_rows;        // blob rows per weight tile index (Cout_pad, or 3 Cout_pad when merged)
-    int dym;                // dy taps merged along N: M tile = 32 rows x 4 columns, one quadrant per column
+    int dxm;                // dx taps merged along N: M tile = 4 rows x 32 columns (30 outputs), one TMEM lane quadrant per row
     int a_stages, b_slots, b_resident, pair;
     int a_plane_bytes;      // (16 MT + 2) * 1024 (16 MT for 1x1)
     int acc_stride, set_stride, bufs, tmem_cols;
@@ -609,7 +676,13 @@ struct Tc2Params {
 
 // PAIR: two CTAs of a cluster issue one cta_group::2 MMA per k-slice (256 pixels x BN): each CTA loads its own A box
 // and HALF of the weight rows, so the per-MMA operand fetch drops from 64 + BN/2 to 64 + BN/4 cycles.
-template <int FLAGS, bool PAIR>
+// DXM (dx taps merged along N, the 64-channel layers and the RGB head): everything about the tile is fixed -- one A box
+// per chunk, three weight tiles (dy), one M tile, one Cout tile -- so the producer and the MMA issuer run straight-line
+// loops in ONE thread each.  These layers have the smallest MMAs (N <= 192), and the generic loops (per-group elect /
+// reconverge, parameter tables in constant memory, a barrier wait per resident weight tile) cost more issue cycles than the
+// MMAs they launch take to execute (ncu: tensor pipe 43% active, issuer warp never waiting).
+// (168 registers is the ceiling for this block: the register file is allocated per 4 warps, so 10 warps cost as much as 12.)
+template <int FLAGS, bool PAIR, bool DXM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -671,10 +744,122 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = s_tmem_base;
-    const int rows_per_set = p.dym ? 30 : 16 * p.MT;         // merged taps: 32 input rows give 30 output rows
-    const int cols_per_tile = p.dym ? 4 * p.MT : 8;
+    const int rows_per_set = DXM ? 4 : 16 * p.MT;
+    const int cols_per_tile = DXM ? 30 : 8;                  // merged taps: 32 input columns give 30 output columns
 
-    if (warp == 0) {
+    if (DXM && warp == 0) {
+        // ================= TMA producer, merged-tap layers =================
+        if (lane == 0) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            bool first_set = true;
+            const int kch = p.kchunks;
+            const uint32_t a_plane = (uint32_t)p.a_plane_bytes;
+            const bool x3 = p.x3 != 0, resident = p.b_resident != 0, lead = !PAIR || cta_rank == 0;
+            const int brow0 = PAIR ? (int)cta_rank * (p.BN / 2) : 0;
+            for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
+                int t = tile;
+                const int bx = ((t % p.tiles_x) * (PAIR ? 2 : 1) + (int)cta_rank) * 30 - 1; t /= p.tiles_x;
+                const int by = (t % p.tiles_y) * 4 - 1;
+                const int n = t / p.tiles_y;
+                for (int kc = 0; kc < kch; ++kc) {
+                    ptx::mbar_wait(ptx::smem_u32(&s_aempty[sa]), pa ^ 1u);
+                    const uint32_t full = ptx::smem_u32(&s_afull[sa]);
+                    const uint32_t dst = smem_base + (uint32_t)sa * a_stage_bytes;
+                    if (lead) ptx::mbar_expect_tx(full, tx_mult * a_stage_bytes);
+                    if (PAIR) {
+                        ptx::tma_load_4d_pair(dst, &map_a_hi, full, kc * BK, bx, by, n);
+                        if (x3) ptx::tma_load_4d_pair(dst + a_plane, &map_a_lo, full, kc * BK, bx, by, n);
+                    } else {
+                        ptx::tma_load_4d(dst, &map_a_hi, full, kc * BK, bx, by, n);
+                        if (x3) ptx::tma_load_4d(dst + a_plane, &map_a_lo, full, kc * BK, bx, by, n);
+                    }
+                    if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+                    if (resident && !first_set) continue;
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        int slot;
+                        if (resident) {
+                            slot = dy * kch + kc;
+                        } else {
+                            slot = sb;
+                            ptx::mbar_wait(ptx::smem_u32(&s_bempty[sb]), pb ^ 1u);
+                            if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
+                        }
+                        const uint32_t bfull = ptx::smem_u32(&s_bfull[slot]);
+                        const uint32_t bdst = b_base + (uint32_t)slot * b_slot_bytes;
+                        const int brow = dy * p.b_tile_rows + brow0;
+                        if (lead) ptx::mbar_expect_tx(bfull, tx_mult * b_slot_bytes);
+                        if (PAIR) {
+                            ptx::tma_load_2d_pair(bdst, &map_b_hi, bfull, kc * BK, brow);
+                            if (x3) ptx::tma_load_2d_pair(bdst + b_plane_bytes, &map_b_lo, bfull, kc * BK, brow);
+                        } else {
+                            ptx::tma_load_2d(bdst, &map_b_hi, bfull, kc * BK, brow);
+                            if (x3) ptx::tma_load_2d(bdst + b_plane_bytes, &map_b_lo, bfull, kc * BK, brow);
+                        }
+                    }
+                }
+                first_set = false;
+            }
+        }
+    } else if (DXM && warp == 1 && cta_rank == 0) {
+        // ================= MMA issuer, merged-tap layers: one thread, 36 (x3) MMAs per chunk back to back =================
+        if (ptx::elect_one()) {
+            const uint32_t idesc = ptx::make_idesc_bf16(PAIR ? 2 * BM : BM, p.BN);
+            int sa = 0, sb = 0, as = 0;
+            uint32_t pa = 0, pb = 0, aphase = 0;
+            bool first_set = true;
+            const int kch = p.kchunks;
+            const uint32_t a_plane = (uint32_t)p.a_plane_bytes;
+            const bool x3 = p.x3 != 0, resident = p.b_resident != 0;
+            for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
+                ptx::mbar_wait(ptx::smem_u32(&s_tempty[as]), aphase ^ 1u);
+                ptx::tc_fence_after();
+                const uint32_t d0 = tmem_base + (uint32_t)(as * p.set_stride);
+                for (int kc = 0; kc < kch; ++kc) {
+                    ptx::mbar_wait(ptx::smem_u32(&s_afull[sa]), pa);
+                    ptx::tc_fence_after();
+                    const uint32_t a_base = smem_base + (uint32_t)sa * a_stage_bytes;
+#pragma unroll
+                    for (int dy = 0; dy < 3; ++dy) {
+                        int slot;
+                        if (resident) {
+                            slot = dy * kch + kc;
+                            if (first_set) {
+                                ptx::mbar_wait(ptx::smem_u32(&s_bfull[slot]), 0u);
+                                ptx::tc_fence_after();
+                            }
+                        } else {
+                            slot = sb;
+                            ptx::mbar_wait(ptx::smem_u32(&s_bfull[sb]), pb);
+                            ptx::tc_fence_after();
+                        }
+                        const uint32_t bs = b_base + (uint32_t)slot * b_slot_bytes;
+                        const uint32_t a0 = a_base + (uint32_t)dy * 4096u;          // tap row dy: 32 pixels x 128 bytes further down the box
+                        const bool overwrite = kc == 0 && dy == 0;
+                        if (PAIR) ptx::mma_kblock_pair(d0, a0, a0 + a_plane, bs, bs + b_plane_bytes, idesc, x3, overwrite);
+                        else ptx::mma_kblock(d0, a0, a0 + a_plane, bs, bs + b_plane_bytes, idesc, x3, overwrite);
+                        if (!resident) {
+                            if (PAIR) ptx::mma_commit_pair(ptx::smem_u32(&s_bempty[sb]));
+                            else ptx::mma_commit(ptx::smem_u32(&s_bempty[sb]));
+                            if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
+                        }
+                    }
+                    if (PAIR) {
+                        ptx::mma_commit_pair(ptx::smem_u32(&s_aempty[sa]));
+                        if (kc == kch - 1) ptx::mma_commit_pair(ptx::smem_u32(&s_tfull[as]));
+                    } else {
+                        ptx::mma_commit(ptx::smem_u32(&s_aempty[sa]));
+                        if (kc == kch - 1) ptx::mma_commit(ptx::smem_u32(&s_tfull[as]));
+                    }
+                    if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+                }
+                first_set = false;
+                if (++as == p.bufs) { as = 0; aphase ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
             int sa = 0, sb = 0;
@@ -695,17 +880,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         const uint32_t full = ptx::smem_u32(&s_afull[sa]);
                         const uint32_t dst = smem_base + (uint32_t)sa * a_stage_bytes;
                         if (!PAIR || cta_rank == 0) ptx::mbar_expect_tx(full, tx_mult * a_stage_bytes);
-                        const int nbox = p.dym ? 4 * p.MT : 1;            // merged taps: one 32-row x 1-column box per quadrant
-                        for (int q = 0; q < nbox; ++q) {
-                            const uint32_t dq = dst + (uint32_t)q * 4096u;
-                            const int cx = bx + q;
-                            if (PAIR) {
-                                ptx::tma_load_4d_pair(dq, &map_a_hi, full, kc * BK, cx, by, n);
-                                if (p.x3) ptx::tma_load_4d_pair(dq + (uint32_t)p.a_plane_bytes, &map_a_lo, full, kc * BK, cx, by, n);
-                            } else {
-                                ptx::tma_load_4d(dq, &map_a_hi, full, kc * BK, cx, by, n);
-                                if (p.x3) ptx::tma_load_4d(dq + (uint32_t)p.a_plane_bytes, &map_a_lo, full, kc * BK, cx, by, n);
-                            }
+                        if (PAIR) {
+                            ptx::tma_load_4d_pair(dst, &map_a_hi, full, kc * BK, bx, by, n);
+                            if (p.x3) ptx::tma_load_4d_pair(dst + (uint32_t)p.a_plane_bytes, &map_a_lo, full, kc * BK, bx, by, n);
+                        } else {
+                            ptx::tma_load_4d(dst, &map_a_hi, full, kc * BK, bx, by, n);
+                            if (p.x3) ptx::tma_load_4d(dst + (uint32_t)p.a_plane_bytes, &map_a_lo, full, kc * BK, bx, by, n);
                         }
                         if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
                         for (int g = 0; g < p.ngrp[ph][j]; ++g) {
@@ -807,7 +987,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int quad = warp & 3;
         const int half = (warp - 2) >> 2;
         const int m = quad * 32 + lane;
-        const int ty = p.dym ? lane : (m >> 3), tx = p.dym ? quad : (m & 7);
+        const int ty = DXM ? quad : (m >> 3), tx = DXM ? lane : (m & 7);
         const int nchunks = (p.BNe + CW - 1) / CW;
         const EpiDev& e = p.ep;
         int as = 0;
@@ -819,33 +999,59 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const int x0 = ((t % p.tiles_x) * (PAIR ? 2 : 1) + (int)cta_rank) * cols_per_tile; t /= p.tiles_x;
             const int y0 = (t % p.tiles_y) * rows_per_set;
             const int n = t / p.tiles_y;
+            // the first chunk's output pixel and residual do not depend on the accumulators: fetch them while the MMAs run
+            constexpr bool kHasResStatic = FLAGS >= 0 && (FLAGS & EPI_RES) != 0;
+            const bool has_res = FLAGS >= 0 ? kHasResStatic : e.res_hi != nullptr;
+            uint4 pre_rh[CW / 8], pre_rl[CW / 8];
+            bool pre = false;
+            if (RRV_EPI_PREFETCH && has_res) {
+                const int iy = y0 + ty, ix = x0 + tx;
+                const bool valid = iy < p.in_H && ix < p.in_W && (!DXM || tx < 30);
+                const int oy = p.nph == 4 ? 2 * iy + (ph >> 1) : iy;
+                const int ox = p.nph == 4 ? 2 * ix + (ph & 1) : ix;
+                const PixCtx px = make_pix(p.o, e, n, oy, ox, valid);
+                const int cb = n0 + half * CW;
+                const bool can = half < nchunks && cb + CW <= p.o.Cout && half * CW + CW <= p.BNe;      // warp-uniform
+                if (RRV_EPI_PREFETCH == 1) {
+                    pre = can;
+                    if (pre && valid) {
+#pragma unroll
+                        for (int g = 0; g < CW / 8; ++g) {
+                            pre_rh[g] = *reinterpret_cast<const uint4*>(e.res_hi + px.res_off + cb + g * 8);
+                            if (e.res_lo) pre_rl[g] = *reinterpret_cast<const uint4*>(e.res_lo + px.res_off + cb + g * 8);
+                        }
+                    }
+                } else if (can && valid) {                 // CW channels = 64 bytes = half a line per plane
+                    ptx::prefetch_l1(e.res_hi + px.res_off + cb);
+                    if (e.res_lo) ptx::prefetch_l1(e.res_lo + px.res_off + cb);
+                }
+            }
             ptx::mbar_wait(ptx::smem_u32(&s_tfull[as]), aphase);
             ptx::tc_fence_after();
             const uint32_t t_set = tmem_base + (uint32_t)(as * p.set_stride) + ((uint32_t)(quad * 32) << 16);
             for (int mt = 0; mt < p.MT; ++mt) {
-                const int iy = y0 + (p.dym ? 0 : 16 * mt) + ty, ix = x0 + (p.dym ? 4 * mt : 0) + tx;
+                const int iy = y0 + (DXM ? 0 : 16 * mt) + ty, ix = x0 + tx;
                 const uint32_t ta = t_set + (uint32_t)(mt * p.acc_stride);
                 if (FLAGS == 0 && p.o.pool) {
                     // fused 2x2 max-pool: the pooled pixel (iy >> 1, ix >> 1); an odd last row / column is dropped (floor)
-                    const bool pvalid = (iy >> 1) < p.o.H && (ix >> 1) < p.o.W && (!p.dym || ty < 30);
+                    const bool pvalid = (iy >> 1) < p.o.H && (ix >> 1) < p.o.W && (!DXM || tx < 30);
                     const PixCtx px = make_pix(p.o, e, n, iy >> 1, ix >> 1, pvalid);
                     float* xbuf = s_tab + (TAB_BYTES / 4) * p.Cout_pad;      // after the constants table (merged-tap layers only)
                     for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4) {
-                        if (p.dym) epilogue_chunk_pool<true>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW,
-                                                             (lane & 1) | ((quad & 1) << 1), xbuf, warp, lane);
+                        if (DXM) epilogue_chunk_pool<true>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW,
+                                                           (lane & 1) | ((quad & 1) << 1), xbuf, warp, lane);
                         else epilogue_chunk_pool<false>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW,
                                                         (lane & 1) | (((lane >> 3) & 1) << 1), xbuf, warp, lane);
                     }
                     continue;
                 }
-                const bool valid = iy < p.in_H && ix < p.in_W && (!p.dym || ty < 30);
+                const bool valid = iy < p.in_H && ix < p.in_W && (!DXM || tx < 30);
                 const int oy = p.nph == 4 ? 2 * iy + (ph >> 1) : iy;
                 const int ox = p.nph == 4 ? 2 * ix + (ph & 1) : ix;
                 const PixCtx px = make_pix(p.o, e, n, oy, ox, valid);
-                for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4) {
-                    if (p.dym) epilogue_chunk<FLAGS, true>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, ch * CW, p.BNe);
-                    else epilogue_chunk<FLAGS, false>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, ch * CW, p.BNe);
-                }
+                for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4)
+                    epilogue_chunk<FLAGS, DXM>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, ch * CW, p.BNe,
+                                               pre && mt == 0 && ch == half, pre_rh, pre_rl);
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -867,7 +1073,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     }
 }
 
-// ---- weight repack: OIHW fp32 -> [tap][Cout_pad][Cin] bf16 hi / lo (3x3: tap = dx*3 + dy) -------------
+// ---- weight repack: OIHW fp32 -> [tap][Cout_pad][Cin] bf16 hi / lo (3x3: tap = dy*3 + dx) -------------
 __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ w, int Cin, int Cout, int Cout_pad, int ksize,
                                                       int ups, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
     const int ntaps = ups ? 16 : ksize * ksize;
@@ -880,8 +1086,8 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const float* __restrict__ 
         if (co < Cout) {
             const float* wk = w + ((long long)co * Cin + ci) * ksize * ksize;
             if (!ups) {
-                // 3x3: blob tap t = dx * 3 + dy (dx-major, so the three dy taps of one dx are adjacent rows)
-                v = ksize == 3 ? wk[(t % 3) * 3 + t / 3] : wk[t];
+                // 3x3: blob tap t = dy * 3 + dx (PyTorch order: the three dx taps of one dy are adjacent row blocks)
+                v = wk[t];
             } else {
                 // phase (py,px), tap (a,b): sum of the 3x3 weights whose upsampled sample falls on
                 // low-res offset (py-1+a, px-1+b):  floor((py + dy - 1) / 2) == py - 1 + a
@@ -997,17 +1203,17 @@ int launch_tc1(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, co
     return check_launch("conv_tc_kernel");
 }
 
-template <int FLAGS, bool PAIR>
+template <int FLAGS, bool PAIR, bool DXM>
 int launch_tc2p(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
                 const CUtensorMap& mb_lo, const Tc2Params& d) {
     static bool attr_set = false;
     if (!attr_set) {
-        const cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<FLAGS, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+        const cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<FLAGS, PAIR, DXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
         RRV_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(conv_tc2_kernel): %s", cudaGetErrorString(e));
         attr_set = true;
     }
     if (!PAIR) {
-        conv_tc2_kernel<FLAGS, PAIR><<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, d);
+        conv_tc2_kernel<FLAGS, PAIR, DXM><<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, d);
     } else {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
@@ -1021,7 +1227,7 @@ int launch_tc2p(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, c
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<FLAGS, PAIR>, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<FLAGS, PAIR, DXM>, ma_hi, ma_lo, mb_hi, mb_lo, d);
         RRV_REQUIRE(e == cudaSuccess, "cudaLaunchKernelEx(conv_tc2_kernel, cluster 2): %s", cudaGetErrorString(e));
     }
     return check_launch("conv_tc2_kernel");
@@ -1030,8 +1236,8 @@ int launch_tc2p(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, c
 template <int FLAGS>
 int launch_tc2(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
                const CUtensorMap& mb_lo, const Tc2Params& d) {
-    return d.pair ? launch_tc2p<FLAGS, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d)
-                  : launch_tc2p<FLAGS, false>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+    return d.pair ? launch_tc2p<FLAGS, true, false>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d)
+                  : launch_tc2p<FLAGS, false, false>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
 }
 
 int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
@@ -1052,47 +1258,45 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     const int btiles_tile = ups ? 4 : btiles;               // ... of which one tile (= one phase) uses this many
 
     int a_stage = 0, b_slot = 0, box_w = 8, box_rows = 0;
-    d.dym = (g_tune.dym && p->ksize == 3 && !ups && 3 * d.Cout_pad <= 256 && d.in_H >= 8) ? 1 : 0;
-    const int xchg_bytes = (p->pool && d.dym) ? EPI_WARPS * 2048 : 0;      // column-partner exchange of the fused max-pool
+    d.dxm = (g_tune.dxm && p->ksize == 3 && !ups && 3 * d.Cout_pad <= 256 && d.in_W >= 16) ? 1 : 0;
+    const int xchg_bytes = (p->pool && d.dxm) ? EPI_WARPS * 512 : 0;       // row-partner exchange of the fused max-pool
     const int budget = SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES - xchg_bytes;
-    if (d.dym) {
-        // ---- merged dy taps: N = 3 Cout_pad, M tile = 32 input rows x 4 columns (one TMEM lane quadrant per column) ----
-        const int MT = 1;
-        d.MT = MT;
+    if (d.dxm) {
+        // ---- merged dx taps: N = 3 Cout_pad, M tile = 4 rows x 32 input columns (one TMEM lane quadrant per row).  ONE A box
+        //      of 6 rows x 32 columns per chunk serves all nine taps: tap row dy reads it from row dy (a 4096-byte offset, whole
+        //      swizzle atoms), the three dx taps are the three column blocks of the weight tile and meet in the epilogue. ----
+        d.MT = 1;
         d.BN = 3 * d.Cout_pad; d.BNe = d.Cout_pad; d.b_tile_rows = 3 * d.Cout_pad;
         d.n_ntiles = 1;
         // (the RGB head, N = 48, stays single-CTA unless pair_min_bn is lowered: each CTA of a pair holds BN / 2 weight rows)
         d.pair = (g_tune.pair && num_sms() % 2 == 0 && d.BN >= g_tune.pair_min_bn && (d.BN / 2) % 8 == 0) ? 1 : 0;
-        a_stage = planes * MT * 16384;
+        d.a_plane_bytes = 6 * 4096;
+        a_stage = planes * d.a_plane_bytes;
         b_slot = planes * d.BN * 128 / (d.pair ? 2 : 1);
-        d.a_plane_bytes = MT * 16384;
         d.acc_stride = (d.BN + 31) / 32 * 32;
-        d.set_stride = MT * d.acc_stride;
+        d.set_stride = d.acc_stride;
         d.bufs = 2 * d.set_stride <= 512 ? 2 : 1;
         d.tmem_cols = 32;
         while (d.tmem_cols < d.bufs * d.set_stride) d.tmem_cols *= 2;
         const int b_all = 3 * d.kchunks;
         if (b_all <= MAX_B_SLOTS && b_all * b_slot + 2 * a_stage <= budget) {
             d.b_resident = 1; d.b_slots = b_all;
-            d.a_stages = std::min(6, (budget - b_all * b_slot) / a_stage);
+            d.a_stages = std::min(MAX_STAGES, (budget - b_all * b_slot) / a_stage);
         } else {
             d.b_resident = 0; d.a_stages = 2; d.b_slots = 2;
             int rem = budget - 2 * a_stage - 2 * b_slot;
             RRV_REQUIRE(rem >= 0, "rrv_conv2d(tcgen05 v2): merged-tap tile does not fit shared memory");
             for (;;) {
-                if (d.b_slots < 3 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
+                if (d.b_slots < 6 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
                 if (d.a_stages < 4 && rem >= a_stage) { ++d.a_stages; rem -= a_stage; continue; }
                 break;
             }
         }
-        d.nA = 3; d.a_y0[0] = -1;
-        for (int j = 0; j < 3; ++j) {
-            d.a_dx[0][j] = j - 1; d.ngrp[0][j] = 1;
-            d.grp[0][j][0] = Grp{j, 0, j == 0 ? 1 : 0};       // weight tile j = the three dy taps of dx = j - 1
-        }
-        box_w = 1; box_rows = 32;
-        d.tiles_x = ceil_div(d.in_W, 4 * MT * (d.pair ? 2 : 1));
-        d.tiles_y = ceil_div(d.in_H, 30);
+        d.nA = 1; d.a_y0[0] = -1; d.a_dx[0][0] = -1; d.ngrp[0][0] = 3;
+        for (int dy = 0; dy < 3; ++dy) d.grp[0][0][dy] = Grp{dy, 4 * dy, dy == 0 ? 1 : 0};   // weight tile dy = the three dx taps of row dy
+        box_w = 32; box_rows = 6;
+        d.tiles_x = ceil_div(d.in_W, 30 * (d.pair ? 2 : 1));
+        d.tiles_y = ceil_div(d.in_H, 4);
     } else {
         // ---- tile shape: Cout tile BN, M tiles per weight tile MT ----
         int BN = std::min(d.Cout_pad, g_tune.max_bn);
@@ -1159,7 +1363,7 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
             d.nA = 3; d.a_y0[0] = -1;
             for (int j = 0; j < 3; ++j) {
                 d.a_dx[0][j] = j - 1; d.ngrp[0][j] = 3;
-                for (int dy = 0; dy < 3; ++dy) d.grp[0][j][dy] = Grp{j * 3 + dy, dy, (j == 0 && dy == 0) ? 1 : 0};
+                for (int dy = 0; dy < 3; ++dy) d.grp[0][j][dy] = Grp{dy * 3 + j, dy, (j == 0 && dy == 0) ? 1 : 0};
             }
         } else {
             // phase (py, px) of the nearest-x2 convolution = a 2x2 convolution over the low-res input with taps at rows
@@ -1202,6 +1406,18 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     const int smem = d.a_stages * a_stage + d.b_slots * b_slot + d.Cout_pad * TAB_BYTES + xchg_bytes + 1024;
     const int flags = epi_flags(p->ep);
     const int grid = d.pair ? 2 * std::min(d.total_tiles, num_sms() / 2) : std::min(d.total_tiles, num_sms());
+    if (d.dxm) {
+        // merged-tap layers: conv1_2 (bias + ReLU [+ pool]), slice2.conv2 (the full chain), the RGB head / anything else (generic)
+        const int f = (flags == 0 || flags == (EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF)) ? flags : -1;
+        if (d.pair) {
+            if (f == 0) return launch_tc2p<0, true, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+            if (f > 0) return launch_tc2p<EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF, true, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+            return launch_tc2p<-1, true, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        }
+        if (f == 0) return launch_tc2p<0, false, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        if (f > 0) return launch_tc2p<EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF, false, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        return launch_tc2p<-1, false, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+    }
     switch (flags) {
         case 0: return launch_tc2<0>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
         case EPI_N1: return launch_tc2<EPI_N1>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
@@ -1233,7 +1449,7 @@ int tc_tune_pair(int enable, int min_bn) {
 }
 
 int tc_tune_merge(int enable) {
-    g_tune.dym = enable ? 1 : 0;
+    g_tune.dxm = enable ? 1 : 0;
     return 0;
 }
 
