@@ -82,6 +82,8 @@ typedef struct rrv_conv {
     void* out_lo;           /* NULL: bf16 mode */
     float* out_f32;         /* NHWC [N][H][W][Cout], or NCHW [N][out_C][H][W] */
     int32_t out_C;          /* channels kept for RRV_OUT_F32_NCHW (3 for the RGB head) */
+    int32_t Cin_used;       /* 0, or the number of leading input channels that meet non-zero weights (KernelFilter's 32
+                             * channels are carried padded to 64: Cin = 64, Cin_used = 32); the rest is not multiplied */
     int32_t pool;           /* 1: nn.MaxPool2d(2, 2) (vgg19.features[4|9|18], floor) fused behind bias + activation; the
                              * planes output is [N][H/2][W/2][Cout].  tcgen05 path, ups == 0, Cout % 32 == 0, no norm /
                              * residual / affine stage. */

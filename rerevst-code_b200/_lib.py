@@ -30,7 +30,7 @@ class Conv(C.Structure):
     _fields_ = [("N", _i32), ("H", _i32), ("W", _i32), ("Cin", _i32), ("Cout", _i32), ("ksize", _i32),
                 ("ups", _i32), ("in_hi", _vp), ("in_lo", _vp), ("w_f32", _vp), ("w_tc", _vp),
                 ("ep", Epilogue), ("out_mode", _i32), ("out_hi", _vp), ("out_lo", _vp), ("out_f32", _vp),
-                ("out_C", _i32), ("pool", _i32)]
+                ("out_C", _i32), ("Cin_used", _i32), ("pool", _i32)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/rerevst_b200.h

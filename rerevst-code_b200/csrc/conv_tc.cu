@@ -37,6 +37,9 @@
 #ifndef RRV_EPI_HALF16
 #define RRV_EPI_HALF16 1        // merged-tap epilogue: combine the three taps 16 columns at a time (register pressure)
 #endif
+#ifndef RRV_EPI_RESVOL
+#define RRV_EPI_RESVOL 1        // residual loads as volatile asm at the top of the chunk
+#endif
 #ifndef RRV_EPI_FOLD
 #define RRV_EPI_FOLD 1          // norm stages as one FMA + clamps with pre-multiplied constants
 #endif
@@ -330,6 +333,28 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
                                                const PixCtx& px, int cb, int col0, int BN, bool pre = false,
                                                const uint4* pre_rh = nullptr, const uint4* pre_rl = nullptr) {
     const bool has_res = FLAGS >= 0 ? (FLAGS & EPI_RES) != 0 : e.res_hi != nullptr;
+    // the residual of the whole chunk goes in flight first, ahead of the TMEM loads and the tap combine (volatile loads: the
+    // compiler would otherwise sink them to their first use to save registers, and the chain then waits for L2)
+    uint4 rh[CW / 8], rl[CW / 8];
+    const bool full = cb + CW <= o.Cout && col0 + CW <= BN;        // warp-uniform
+    if (pre) {                                                     // loaded by the caller while the MMAs were still running
+#pragma unroll
+        for (int g = 0; g < CW / 8; ++g) {
+            rh[g] = pre_rh[g];
+            rl[g] = pre_rl[g];
+        }
+    } else if (has_res && px.valid && full) {
+#pragma unroll
+        for (int g = 0; g < CW / 8; ++g) {
+#if RRV_EPI_RESVOL
+            rh[g] = ptx::ldg_nc_v4(e.res_hi + px.res_off + cb + g * 8);
+            if (e.res_lo) rl[g] = ptx::ldg_nc_v4(e.res_lo + px.res_off + cb + g * 8);
+#else
+            rh[g] = *reinterpret_cast<const uint4*>(e.res_hi + px.res_off + cb + g * 8);
+            if (e.res_lo) rl[g] = *reinterpret_cast<const uint4*>(e.res_lo + px.res_off + cb + g * 8);
+#endif
+        }
+    }
     uint32_t r[CW];
     if (DXM && RRV_EPI_HALF16) {
 #pragma unroll
@@ -365,22 +390,6 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
             const float b = __shfl_down_sync(0xffffffffu, __uint_as_float(r1[i]), 1);
             const float c = __shfl_down_sync(0xffffffffu, __uint_as_float(r2[i]), 2);
             r[i] = __float_as_uint((a + b) + c);
-        }
-    }
-    // the residual of the whole chunk goes in flight while the TMEM load completes
-    uint4 rh[CW / 8], rl[CW / 8];
-    const bool full = cb + CW <= o.Cout && col0 + CW <= BN;        // warp-uniform
-    if (pre) {                                                     // loaded by the caller while the MMAs were still running
-#pragma unroll
-        for (int g = 0; g < CW / 8; ++g) {
-            rh[g] = pre_rh[g];
-            rl[g] = pre_rl[g];
-        }
-    } else if (has_res && px.valid && full) {
-#pragma unroll
-        for (int g = 0; g < CW / 8; ++g) {
-            rh[g] = *reinterpret_cast<const uint4*>(e.res_hi + px.res_off + cb + g * 8);
-            if (e.res_lo) rl[g] = *reinterpret_cast<const uint4*>(e.res_lo + px.res_off + cb + g * 8);
         }
     }
     if (!DXM) ptx::tmem_ld32_wait(r);
@@ -656,6 +665,7 @@ struct Tc2Params {
     OutDesc o;
     int N, in_H, in_W;
     int Cout, Cout_pad, kchunks;
+    int nk_last;            // k-slices (of 16 channels) of the last chunk that meet non-zero weights (rrv_conv.Cin_used), 1..4
     int nph;                // 1, or 4 output phases of a nearest-x2 convolution (each phase is its own tile)
     int MT;
     int nA;                 // A boxes per chunk: 3 (3x3), 2 (one ups phase), 1 (1x1)
@@ -837,8 +847,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         const uint32_t bs = b_base + (uint32_t)slot * b_slot_bytes;
                         const uint32_t a0 = a_base + (uint32_t)dy * 4096u;          // tap row dy: 32 pixels x 128 bytes further down the box
                         const bool overwrite = kc == 0 && dy == 0;
-                        if (PAIR) ptx::mma_kblock_pair(d0, a0, a0 + a_plane, bs, bs + b_plane_bytes, idesc, x3, overwrite);
-                        else ptx::mma_kblock(d0, a0, a0 + a_plane, bs, bs + b_plane_bytes, idesc, x3, overwrite);
+                        const uint32_t nk = kc == kch - 1 ? (uint32_t)p.nk_last : 4u;
+                        if (PAIR) ptx::mma_kblock_pair(d0, a0, a0 + a_plane, bs, bs + b_plane_bytes, idesc, x3, overwrite, nk);
+                        else ptx::mma_kblock(d0, a0, a0 + a_plane, bs, bs + b_plane_bytes, idesc, x3, overwrite, nk);
                         if (!resident) {
                             if (PAIR) ptx::mma_commit_pair(ptx::smem_u32(&s_bempty[sb]));
                             else ptx::mma_commit(ptx::smem_u32(&s_bempty[sb]));
@@ -946,18 +957,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         const uint32_t a0 = a_base + (uint32_t)(gr.arow * 1024);
                         const uint32_t d0 = d_set;
                         const uint32_t bempty_bar = ptx::smem_u32(&s_bempty[sb]);
+                        const uint32_t nk = kc == p.kchunks - 1 ? (uint32_t)p.nk_last : 4u;
                         if (ptx::elect_one()) {
                             if (PAIR) {
-                                ptx::mma_kblock_pair(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
+                                ptx::mma_kblock_pair(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, p.x3 != 0, overwrite, nk);
                                 if (p.MT == 2)
                                     ptx::mma_kblock_pair(d0 + (uint32_t)p.acc_stride, a0 + 16384u, a0 + 16384u + (uint32_t)p.a_plane_bytes, bs,
-                                                         bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
+                                                         bs + b_plane_bytes, idesc, p.x3 != 0, overwrite, nk);
                                 if (!p.b_resident) ptx::mma_commit_pair(bempty_bar);
                             } else {
-                                ptx::mma_kblock(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
+                                ptx::mma_kblock(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, p.x3 != 0, overwrite, nk);
                                 if (p.MT == 2)
                                     ptx::mma_kblock(d0 + (uint32_t)p.acc_stride, a0 + 16384u, a0 + 16384u + (uint32_t)p.a_plane_bytes, bs,
-                                                    bs + b_plane_bytes, idesc, p.x3 != 0, overwrite);
+                                                    bs + b_plane_bytes, idesc, p.x3 != 0, overwrite, nk);
                                 if (!p.b_resident) ptx::mma_commit(bempty_bar);
                             }
                         }
@@ -1250,6 +1262,11 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     d.Cout = p->Cout;
     d.Cout_pad = cout_pad_of(p->Cout);
     d.kchunks = p->Cin / BK;
+    d.nk_last = 4;
+    if (p->Cin_used > 0 && p->Cin_used < p->Cin) {      // trailing input channels that only meet zero weights: whole chunks, then k-slices
+        d.kchunks = (p->Cin_used + BK - 1) / BK;
+        d.nk_last = (p->Cin_used - (d.kchunks - 1) * BK + 15) / 16;
+    }
     d.x3 = p->in_lo != nullptr;
     d.nph = ups ? 4 : 1;
     const int halo = (p->ksize == 3) ? 1 : 0;

@@ -148,15 +148,27 @@ __global__ void __launch_bounds__(256) first_layer_kernel(const FirstDev p) {
 // pixels fix up by subtracting the W0 of their missing taps.  3x fewer FMAs: the kernel becomes store-bound.
 constexpr float GRAY_GM = 0.449f, GRAY_GS = 0.226f;
 
+constexpr int FL_TPB = 4;      // consecutive tiles (along x) per block: the weight tables are built once per block
+
+__device__ __forceinline__ float gray_u(const FirstDev& p, int n, int y, int x) {
+    if (y < 0 || y >= p.H || x < 0 || x >= p.W) return 0.0f;
+    float v[3];
+    load_normalised(p, n, y, x, v);
+    return (gray_value(v) - GRAY_GM) * (1.0f / GRAY_GS);
+}
+
 __global__ void __launch_bounds__(256) first_layer_gray_kernel(const FirstDev p) {
     constexpr int PH = FL_TH + 2, PW = FL_TW + 2;
-    __shared__ float s_in[PH][PW + 2];
+    __shared__ float s_in[2][PH][PW + 2];
     __shared__ __align__(16) float s_w1[9][64];
     __shared__ __align__(16) float s_w0[9][64];
     __shared__ float s_b[64];
     const int tid = threadIdx.x;
     const int tiles_x = (p.W + FL_TW - 1) / FL_TW;
-    const int oy0 = (blockIdx.x / tiles_x) * FL_TH, ox0 = (blockIdx.x % tiles_x) * FL_TW;
+    const int groups_x = (tiles_x + FL_TPB - 1) / FL_TPB;
+    const int oy0 = (blockIdx.x / groups_x) * FL_TH;
+    const int tx0 = (blockIdx.x % groups_x) * FL_TPB;
+    const int ntile = min(FL_TPB, tiles_x - tx0);
     const int n = blockIdx.y;
     const float mean[3] = {0.485f, 0.456f, 0.406f};
     const float sd[3] = {0.229f, 0.224f, 0.225f};
@@ -173,16 +185,14 @@ __global__ void __launch_bounds__(256) first_layer_gray_kernel(const FirstDev p)
         s_w1[t][co] = w1;
         s_w0[t][co] = w0;
     }
-    for (int i = tid; i < PH * PW; i += 256) {
-        const int r = i / PW, c = i % PW;
-        const int y = oy0 - 1 + r, x = ox0 - 1 + c;
-        float u = 0.0f;
-        if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
-            float v[3];
-            load_normalised(p, n, y, x, v);
-            u = (gray_value(v) - GRAY_GM) * (1.0f / GRAY_GS);
-        }
-        s_in[r][c] = u;
+    // halo pixels of a tile handled by this thread: tid and tid + 256 (PH * PW = 340)
+    const int h0r = tid / PW, h0c = tid % PW;
+    const int h1 = tid + 256, h1r = h1 / PW, h1c = h1 % PW;
+    const bool has1 = h1 < PH * PW;
+    {
+        const int ox0 = tx0 * FL_TW;
+        s_in[0][h0r][h0c] = gray_u(p, n, oy0 - 1 + h0r, ox0 - 1 + h0c);
+        if (has1) s_in[0][h1r][h1c] = gray_u(p, n, oy0 - 1 + h1r, ox0 - 1 + h1c);
     }
     __syncthreads();
     if (tid < 64) {
@@ -196,56 +206,73 @@ __global__ void __launch_bounds__(256) first_layer_gray_kernel(const FirstDev p)
     // thread = 8 adjacent pixels x 8 output channels: the 8 lanes of a pixel store one full 128-byte line per plane
     const int q = tid & 7, pg = tid >> 3;
     const int r = pg >> 2, c0 = (pg & 3) * 8;
-    float acc[8][8];
+    const int oy = oy0 + r;
+    const bool edge_row = oy == 0 || oy == p.H - 1;
+    for (int t = 0; t < ntile; ++t) {
+        const int ox0 = (tx0 + t) * FL_TW;
+        const int buf = t & 1;
+        // the next tile's halo goes in flight before this tile's arithmetic
+        float nx0 = 0.0f, nx1 = 0.0f;
+        const bool more = t + 1 < ntile;
+        if (more) {
+            nx0 = gray_u(p, n, oy0 - 1 + h0r, ox0 + FL_TW - 1 + h0c);
+            if (has1) nx1 = gray_u(p, n, oy0 - 1 + h1r, ox0 + FL_TW - 1 + h1c);
+        }
+        float acc[8][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc[j][k] = s_b[q * 8 + k];
+            for (int k = 0; k < 8; ++k) acc[j][k] = s_b[q * 8 + k];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-        float a[10];
+        for (int dy = 0; dy < 3; ++dy) {
+            float a[10];
 #pragma unroll
-        for (int i = 0; i < 10; ++i) a[i] = s_in[r + dy][c0 + i];
+            for (int i = 0; i < 10; ++i) a[i] = s_in[buf][r + dy][c0 + i];
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            const float4* wp = reinterpret_cast<const float4*>(&s_w1[dy * 3 + dx][q * 8]);
-            const float4 wa = wp[0], wb = wp[1];
+            for (int dx = 0; dx < 3; ++dx) {
+                const float4* wp = reinterpret_cast<const float4*>(&s_w1[dy * 3 + dx][q * 8]);
+                const float4 wa = wp[0], wb = wp[1];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    acc[j][0] = fmaf(a[j + dx], wa.x, acc[j][0]);
+                    acc[j][1] = fmaf(a[j + dx], wa.y, acc[j][1]);
+                    acc[j][2] = fmaf(a[j + dx], wa.z, acc[j][2]);
+                    acc[j][3] = fmaf(a[j + dx], wa.w, acc[j][3]);
+                    acc[j][4] = fmaf(a[j + dx], wb.x, acc[j][4]);
+                    acc[j][5] = fmaf(a[j + dx], wb.y, acc[j][5]);
+                    acc[j][6] = fmaf(a[j + dx], wb.z, acc[j][6]);
+                    acc[j][7] = fmaf(a[j + dx], wb.w, acc[j][7]);
+                }
+            }
+        }
+        if (oy < p.H) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                acc[j][0] = fmaf(a[j + dx], wa.x, acc[j][0]);
-                acc[j][1] = fmaf(a[j + dx], wa.y, acc[j][1]);
-                acc[j][2] = fmaf(a[j + dx], wa.z, acc[j][2]);
-                acc[j][3] = fmaf(a[j + dx], wa.w, acc[j][3]);
-                acc[j][4] = fmaf(a[j + dx], wb.x, acc[j][4]);
-                acc[j][5] = fmaf(a[j + dx], wb.y, acc[j][5]);
-                acc[j][6] = fmaf(a[j + dx], wb.z, acc[j][6]);
-                acc[j][7] = fmaf(a[j + dx], wb.w, acc[j][7]);
+                const int ox = ox0 + c0 + j;
+                if (ox >= p.W) continue;
+                if (edge_row || ox == 0 || ox == p.W - 1) {       // taps that fall outside the image carry no W0 term
+                    for (int tp = 0; tp < 9; ++tp) {
+                        const int y = oy + tp / 3 - 1, x = ox + tp % 3 - 1;
+                        if (y >= 0 && y < p.H && x >= 0 && x < p.W) continue;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[j][k] -= s_w0[tp][q * 8 + k];
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[j][k] = fmaxf(acc[j][k], 0.0f);
+                const long long o = (((long long)n * p.H + oy) * p.W + ox) * 64 + q * 8;
+                if (p.out_hi != nullptr) store8(p.out_hi + o, p.out_lo ? p.out_lo + o : nullptr, p.lo_fp16, acc[j]);
+                if (p.out_f32 != nullptr) {
+                    *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                    *reinterpret_cast<float4*>(p.out_f32 + o + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+                }
             }
         }
-    }
-    const int oy = oy0 + r;
-    if (oy >= p.H) return;
-    const bool edge_row = oy == 0 || oy == p.H - 1;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int ox = ox0 + c0 + j;
-        if (ox >= p.W) continue;
-        if (edge_row || ox == 0 || ox == p.W - 1) {       // taps that fall outside the image carry no W0 term
-            for (int t = 0; t < 9; ++t) {
-                const int y = oy + t / 3 - 1, x = ox + t % 3 - 1;
-                if (y >= 0 && y < p.H && x >= 0 && x < p.W) continue;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) acc[j][k] -= s_w0[t][q * 8 + k];
-            }
+        if (more) {                       // the other buffer was last read two iterations ago (one barrier in between)
+            s_in[buf ^ 1][h0r][h0c] = nx0;
+            if (has1) s_in[buf ^ 1][h1r][h1c] = nx1;
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[j][k] = fmaxf(acc[j][k], 0.0f);
-        const long long o = (((long long)n * p.H + oy) * p.W + ox) * 64 + q * 8;
-        if (p.out_hi != nullptr) store8(p.out_hi + o, p.out_lo ? p.out_lo + o : nullptr, p.lo_fp16, acc[j]);
-        if (p.out_f32 != nullptr) {
-            *reinterpret_cast<float4*>(p.out_f32 + o) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-            *reinterpret_cast<float4*>(p.out_f32 + o + 4) = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
-        }
+        __syncthreads();
     }
 }
 
@@ -258,7 +285,8 @@ int first_layer(const void* src, int src_kind, int gray, int N, int H, int W, co
     FirstDev d{src, w, bias, (uint16_t*)out_hi, (uint16_t*)out_lo, out_f32, N, H, W, src_kind, gray, g_lo_fp16};
     dim3 grid(ceil_div(W, FL_TW) * ceil_div(H, FL_TH), N);
     if (gray) {
-        first_layer_gray_kernel<<<grid, 256, 0, st>>>(d);
+        dim3 ggrid(ceil_div(ceil_div(W, FL_TW), FL_TPB) * ceil_div(H, FL_TH), N);
+        first_layer_gray_kernel<<<ggrid, 256, 0, st>>>(d);
         return check_launch("first_layer_gray_kernel");
     }
     first_layer_kernel<<<grid, 256, 0, st>>>(d);

@@ -63,6 +63,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+__device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ---- TMA -------------------------------------------------------------------------------------
@@ -126,11 +131,13 @@ __device__ __forceinline__ void mma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint
 }
 // One 64-channel k-block (4 k-slices of 16) of one 128-row M tile against one weight tile.
 // Addresses are shared-memory byte addresses of the hi / lo operand planes; called by ONE thread.
+// nk < 4: only the first nk k-slices carry non-zero weights (input channels padded up to the 64-channel chunk).
 __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                           uint32_t idesc, bool x3, bool overwrite) {
+                                           uint32_t idesc, bool x3, bool overwrite, uint32_t nk = 4) {
     const uint32_t ah = desc_lo_sw128(a_hi), al = desc_lo_sw128(a_lo), bh = desc_lo_sw128(b_hi), bl = desc_lo_sw128(b_lo);
 #pragma unroll
     for (uint32_t k = 0; k < 4; ++k) {           // 16 bf16 = 32 bytes = 2 descriptor units per k-slice
+        if (k >= nk) break;
         mma_bf16_lo(d_tmem, ah + 2 * k, bh + 2 * k, idesc, (overwrite && k == 0) ? 0u : 1u);
         if (x3) {
             mma_bf16_lo(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1u);
@@ -205,10 +212,11 @@ __device__ __forceinline__ void mma_bf16_lo_pair(uint32_t d_tmem, uint32_t a_lo,
         : "memory");
 }
 __device__ __forceinline__ void mma_kblock_pair(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                                uint32_t idesc, bool x3, bool overwrite) {
+                                                uint32_t idesc, bool x3, bool overwrite, uint32_t nk = 4) {
     const uint32_t ah = desc_lo_sw128(a_hi), al = desc_lo_sw128(a_lo), bh = desc_lo_sw128(b_hi), bl = desc_lo_sw128(b_lo);
 #pragma unroll
     for (uint32_t k = 0; k < 4; ++k) {
+        if (k >= nk) break;
         mma_bf16_lo_pair(d_tmem, ah + 2 * k, bh + 2 * k, idesc, (overwrite && k == 0) ? 0u : 1u);
         if (x3) {
             mma_bf16_lo_pair(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1u);

@@ -62,6 +62,7 @@ class ConvW:
             wp[:cout, :cin] = w
             w = wp
         self.Cin, self.Cout, self.ksize, self.ups = cin_p, cout_p, k, bool(ups)
+        self.Cin_used = cin if cin_p != cin else 0       # zero-padded input channels are not multiplied
         self.bias = None
         if bias is not None:
             self.bias = torch.zeros(cout_p, dtype=torch.float32, device=w.device)
@@ -180,6 +181,7 @@ class StyleEngine:
         d.ep = ep
         d.out_mode = out_mode
         d.pool = int(pool)
+        d.Cin_used = cw.Cin_used
         if out_mode == L.OUT_PLANES:
             out = out or Planes(N, H >> int(pool), W >> int(pool), cw.Cout, self.x3, self.device)
             d.out_hi, d.out_lo = L.ptr(out.hi), L.ptr(out.lo)
