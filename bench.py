@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--kernels", default=os.environ.get("RRV_KERNELS", "auto"), choices=["auto", "ffma", "tc"])
     ap.add_argument("--samples", type=int, default=4, help="sampled frames of the pre-pass (not timed)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bf16", action="store_true", help="skip the bf16 (BASELINE config 3) side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -297,6 +298,22 @@ def main():
     conv_ms = sum(t for _, t, _ in layers)
     conv_flops = sum(f for _, _, f in layers)
 
+    # ---- BASELINE config 3 beside it: bf16 operands (hi planes only), fp32 accumulate and fp32 statistics.  Not the headline:
+    #      on this network plain bf16 operands miss the 1e-3 parity bar (see "parity" below), the x3 split meets it. ----
+    bf16 = None
+    if args.precision == "x3" and not args.no_bf16:
+        fw16 = Stylization(sd, cuda=True, precision="bf16", impl=args.kernels)
+        eng16 = fw16.model._eng()
+        fw16.prepare_style(style)
+        eng16.import_clip_state(eng.export_clip_state())         # same per-clip statistics and filters
+        ms16, _ = timed(lambda i: eng16.forward_graphed(dev_frames[i % nfr], kind=1), args.steps, args.warmup)
+        ref32 = eng.forward(dev_frames[0], kind=1)
+        got16 = eng16.forward(dev_frames[0], kind=1)
+        err16 = float((got16 - ref32).abs().max() / ref32.abs().max())
+        bf16 = (ms16, err16)
+        del fw16, eng16, ref32, got16
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -337,6 +354,12 @@ def main():
                             "traffic = DRAM bytes per launch, mean over the frame's conv launches, from profiles/r1_traffic.json",
                      "launches_per_frame": len(layers), "kernel_ms_per_frame": conv_ms,
                      "whole_frame": {"achieved": frame_tflops, "frac": frame_tflops / pk["tflops"], "flops_per_frame": fl}},
+        "config3_bf16": None if bf16 is None else {
+            "value": world * args.steps / (bf16[0] * 1e-3), "unit": "frames/s", "ms_per_step": bf16[0] / args.steps,
+            "whole_frame_roofline_frac": fl * (args.steps / (bf16[0] * 1e-3)) / 1e12 / pk["tflops"],
+            "rel_linf_vs_x3_same_frame": bf16[1],
+            "note": "bf16 operands, fp32 accumulate / statistics / epilogue (BASELINE.json configs[2]); not the headline because "
+                    "it does not meet the 1e-3 parity bar on this network"},
         "prepass_s": prepass_s,
         "layers": [{"layer": lbl, "ms": round(t, 4), "tflops": round(f / (t * 1e-3) / 1e12, 2) if t > 0 else None}
                    for lbl, t, f in layers],

@@ -132,6 +132,27 @@ def run_warp():
     return res, meta
 
 
+def run_train(sd):
+    """train/style_networks.py: validation (frame mode without RGB2Gray, :556-559), the Vgg19 loss network (:284-314) and
+    style_loss / content_loss (:503-516) on the temporal-loss path of train/train.py:375-388."""
+    m = import_reference("style_networks", "train")
+    net = m.TransformerNet().eval()
+    net.load_state_dict(sd, strict=True)
+    style, frame = cases.frame_inputs("frame_small")
+    g = torch.Generator().manual_seed(4321)
+    other = torch.randn(2, 3, 40, 56, generator=g)
+    with torch.no_grad():
+        out = net.validation(frame, style)
+        f_a = net.Vgg19(other)
+        f_b = net.Vgg19(torch.flip(other, dims=(0, 3)))
+        res = {"validation": out.numpy(), "style_loss": np.array(float(net.style_loss(f_a, f_b)), np.float64),
+               "content_loss": np.array(float(net.content_loss(f_a, f_b)), np.float64), "relu4_1": f_a.relu4_1.numpy()}
+        for lvl, ft in zip(f_a._fields, f_a):
+            mean, std = m.calc_mean_std(ft)
+            res[f"mean/{lvl}"], res[f"std/{lvl}"] = mean.numpy(), std.numpy()
+    return res
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sd = synthetic_state_dict(cases.WEIGHT_SEED)
@@ -143,6 +164,7 @@ def main():
         print(name, {k: v.shape for k, v in res.items() if not k.startswith("stat")})
     for name in cases.FRAME_CASES:
         np.savez_compressed(os.path.join(OUT, f"frame_{name}.npz"), **run_frame(name, sd))
+    np.savez_compressed(os.path.join(OUT, "train_model.npz"), **run_train(sd))
     res, meta = run_warp()
     np.savez_compressed(os.path.join(OUT, "warp.npz"), **res)
     with open(os.path.join(OUT, "warp_digests.json"), "w") as f:

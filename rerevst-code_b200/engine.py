@@ -138,7 +138,9 @@ class StyleEngine:
         dev = self.device
         g = lambda k: sd[k].detach().to(dev, torch.float32)
         w = {}
-        for top in ("Encoder", "EncoderStyle"):
+        for top in ("Encoder", "EncoderStyle", "Vgg19"):
+            if top == "Vgg19" and vgg_keys(top)[0][0] not in sd:       # deleted after the first style, like the reference
+                continue
             convs = []
             for j, (wk, bk) in enumerate(vgg_keys(top)):
                 if j == 0:
@@ -481,6 +483,114 @@ class StyleEngine:
         graph.replay()
         self.graph_launches += launches
         return g_out
+
+    # ------------------------------------------------------------------ frame mode (use_Global=False) and training-side VGG
+    def _frame_norm(self, x_f32):
+        """Frame-mode InstanceNorm (style_network_frame.py:39-43): per-frame mean / rsqrt(biased var + 1e-8), no clamp.
+        Returns the float[4][C] table {mean, rstd, -inf, +inf} of ONE sample."""
+        Cc = x_f32.shape[-1]
+        part = torch.empty((5, Cc), dtype=torch.float64, device=self.device)
+        L.check(self.lib.rrv_channel_stats(x_f32.data_ptr(), x_f32.numel() // Cc, Cc, part.data_ptr(), L.stream()),
+                "rrv_channel_stats")
+        return self._finalize(part, 3, 1e-8)
+
+    def _style_pred_means(self, f):
+        """mean_hw(F?.down_sample(normalized_style)) of both predictors of a KernelFilter: frame-invariant, cached per style."""
+        cache = self.style.setdefault("pred_means", {})
+        if f not in cache:
+            fw = self.w[f]
+            s = self._conv(fw["pred"], self.style["nstyle"], make_epilogue(bias=fw["pred"].bias), L.OUT_F32_NHWC)
+            part = torch.empty((5, 64), dtype=torch.float64, device=self.device)
+            L.check(self.lib.rrv_channel_stats(s.data_ptr(), s.numel() // 64, 64, part.data_ptr(), L.stream()), "stats")
+            cache[f] = self._finalize(part, 2, 0.0)[0]
+        return cache[f]
+
+    @torch.no_grad()
+    def forward_frame(self, frame, kind=0, gray=True):
+        """TransformerNet.forward of test/style_network_frame.py:392-394 (Decoder.forward :341-358): every InstanceNorm takes
+        its statistics from the frame itself, the six dynamic filters are predicted per frame (FilterPredictor.forward
+        :53-62), AdaIN(relu4_1) follows the filters directly (:339).  gray=False is ``validation`` of
+        train/style_networks.py:556-559.  A batch is processed sample by sample (the statistics are per sample)."""
+        if self.style is None:
+            raise RuntimeError("forward() before generate_style_features()")
+        if kind == 0:
+            N, _, H, W = frame.shape
+        else:
+            N, H, W, _ = frame.shape
+        frame = frame.contiguous()
+        out = torch.empty((N, 3, H, W), dtype=torch.float32, device=self.device)
+        tabs = self.style["tabs"]
+        for i in range(N):
+            x = self._vgg("Encoder", frame[i:i + 1], kind, gray, 1, H, W, "raw")              # fp32 NHWC relu4_1
+            h = self._pointwise(x, make_epilogue(norm1=self._frame_norm(x)))
+            for j, f in enumerate(FILTERS):
+                fw = self.w[f]
+                ep = make_epilogue(bias=fw["pred"].bias)
+                c_mean = self._finalize(self._stats_part(self._conv(fw["pred"], h, ep, L.OUT_F32_NHWC)), 2, 0.0)[0]
+                s_mean = self._style_pred_means(f)
+                wf = []
+                for q, (fcw, fcb) in enumerate(fw["fc"]):
+                    m = torch.empty((32, 32), dtype=torch.float32, device=self.device)
+                    L.check(self.lib.rrv_filter_fc(fcw.data_ptr(), fcb.data_ptr(), c_mean[32 * q:].data_ptr(),
+                                                   s_mean[32 * q:].data_ptr(), m.data_ptr(), L.stream()), "rrv_filter_fc")
+                    wf.append(m)
+                down, up = self._folded(f, wf[0], wf[1])
+                t = self._conv(down, h, make_epilogue(bias=down.bias, act=2))
+                if j < 2:
+                    h = self._conv(up, t, make_epilogue(bias=up.bias, res=h))
+                else:       # results * style_std + style_mean (:339), no second norm in this mode
+                    h = self._conv(up, t, make_epilogue(bias=up.bias, res=h, affine=tabs["relu4_1"]))
+            for block, lvl in (("slice4", "relu3_1"), ("slice3", "relu2_1"), ("slice2", "relu1_1")):
+                bw = self.w[block]
+                s = self._conv(bw["short"], h, make_epilogue())
+                r1 = self._conv(bw["conv1"], h, make_epilogue(bias=bw["conv1"].bias, act=2), L.OUT_F32_NHWC)
+                y = self._pointwise(r1, make_epilogue(norm1=self._frame_norm(r1)))
+                del r1
+                r2 = self._conv(bw["conv2"], y, make_epilogue(bias=bw["conv2"].bias, act=2), L.OUT_F32_NHWC)
+                r = self._pointwise(r2, make_epilogue(norm1=self._frame_norm(r2), res=s, res_shift=1), to_f32=True)
+                del r2
+                h = self._pointwise(r, make_epilogue(norm1=self._frame_norm(r), affine=tabs[lvl]))    # Decoder.AdaIN :311-319
+                del r
+            head = self.w["slice1"]
+            self._conv(head, h, make_epilogue(bias=head.bias), L.OUT_F32_NCHW, out=out[i:i + 1], out_C=3)
+        return out
+
+    def _folded(self, f, wf1, wf2):
+        """The two convolutions of a KernelFilter with its predicted 32x32 matrices folded in (see _fold_filter), without
+        touching the per-clip cache."""
+        fw = self.w[f]
+        dw = torch.matmul(wf1, fw["down_w"].reshape(32, -1)).reshape(32, 512, 3, 3)
+        db = torch.mv(wf1, fw["down_b"])
+        uw = torch.einsum("ojyx,ji->oiyx", fw["up_w"], wf2).contiguous()
+        return ConvW(dw, db, cout_pad=INNER_PAD), ConvW(uw, fw["up_b"], cin_pad=INNER_PAD)
+
+    @torch.no_grad()
+    def vgg_features(self, x, top="Vgg19", kind=0):
+        """Vgg19.forward of train/style_networks.py:284-314 (and EncoderStyle's four taps): relu1_1, relu2_1, relu3_1,
+        relu4_1 as fp32 NCHW views of NHWC tensors, for a batch of normalised RGB images."""
+        if top not in self.w:
+            raise RuntimeError(f"no weights loaded under '{top}.*'")
+        if kind == 0:
+            N, _, H, W = x.shape
+        else:
+            N, H, W, _ = x.shape
+        taps = self._vgg(top, x.contiguous(), kind, False, N, H, W, "style")
+        return tuple(taps[i].permute(0, 3, 1, 2) for i in (0, 5, 10, 19))
+
+    @torch.no_grad()
+    def feature_mean_std(self, feat_nchw_view):
+        """calc_mean_std (train/style_networks.py:95-103) per sample: ([N,C] mean, [N,C] sqrt(unbiased var + 1e-5))."""
+        x = feat_nchw_view.permute(0, 2, 3, 1)
+        assert x.is_contiguous(), "expects the NCHW view of an NHWC tensor as returned by vgg_features"
+        N, Hh, Ww, Cc = x.shape
+        means, stds = [], []
+        for i in range(N):
+            part = torch.empty((5, Cc), dtype=torch.float64, device=self.device)
+            L.check(self.lib.rrv_channel_stats(x[i].data_ptr(), Hh * Ww, Cc, part.data_ptr(), L.stream()), "rrv_channel_stats")
+            t = self._finalize(part, 1, 1e-5)
+            stds.append(t[0])
+            means.append(t[1])
+        return torch.stack(means), torch.stack(stds)
 
     # ------------------------------------------------------------------ state export (tests, dist)
     def export_clip_state(self):

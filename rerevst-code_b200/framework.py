@@ -23,6 +23,7 @@ class Stylization:
             from .style_network_global import TransformerNet
         else:
             from .style_network_frame import TransformerNet
+        self.use_Global = bool(use_Global)
         self.model = TransformerNet(precision=precision, impl=impl).to(self.device)
         sd = checkpoint if isinstance(checkpoint, dict) else torch.load(checkpoint, map_location="cpu")
         self.model.load_state_dict(sd)
@@ -46,6 +47,8 @@ class Stylization:
 
     # ===== Sequence-Level Global Feature Sharing =====
     def add(self, patch):
+        if not self.use_Global:
+            return self.model.add(patch)        # AttributeError, as in the reference (frame mode has no pre-pass)
         eng = self.model._eng()
         if self.model.F_patches is None:
             raise AttributeError("call clean() before add()")
@@ -112,7 +115,7 @@ class Stylization:
                 slot["ev_in"].record(s_in)
             cur.wait_event(slot["ev_in"])
             cur.wait_event(slot["ev_out"])                  # dev_out of this slot has been downloaded
-            net_out = eng.forward_graphed(slot["dev_in"], kind=1)
+            net_out = self._net(eng, slot["dev_in"])
             L.check(L.lib().rrv_postprocess_bgr(net_out.data_ptr(), 1, H, W, y0, x0, h, w, slot["dev_out"].data_ptr(),
                                                 L.stream()), "rrv_postprocess_bgr")
             slot["ev_free"].record(cur)
@@ -125,6 +128,12 @@ class Stylization:
         while pending:
             yield finish(pending.pop(0))
 
+    def _net(self, eng, dev_u8):
+        """uint8 NHWC frame on the device -> fp32 NCHW network output (global mode: one CUDA-graph replay)."""
+        if self.use_Global:
+            return eng.forward_graphed(dev_u8, kind=1)
+        return eng.forward_frame(dev_u8, kind=1, gray=True)
+
     def _side_streams(self):
         if not hasattr(self, "_streams"):
             self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
@@ -132,7 +141,7 @@ class Stylization:
 
     def transfer_device(self, frame, crop=None):
         eng = self.model._eng()
-        y = eng.forward_graphed(self._upload(frame), kind=1)
+        y = self._net(eng, self._upload(frame))
         N, _, H, W = y.shape
         y0, x0, h, w = crop if crop is not None else (0, 0, H, W)
         out = torch.empty((N, h, w, 3), dtype=torch.float32, device=self.device)

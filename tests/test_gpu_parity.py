@@ -323,6 +323,65 @@ def test_global_mode_matches_reference_golden(L, dev, state_dict, name, impl):
     assert rel_linf(out.cpu().numpy(), gold["out"]) < TOL
 
 
+def test_frame_mode_matches_reference_golden(L, dev, state_dict):
+    """use_Global=False (test/style_network_frame.py): per-frame statistics and per-frame dynamic filters."""
+    from oracle import cases
+    from rerevst_code_b200.style_network_frame import TransformerNet
+    gold = np.load(os.path.join(GOLDEN, "frame_frame_small.npz"))
+    style, frame = cases.frame_inputs("frame_small")
+    net = TransformerNet().to(dev)
+    net.load_state_dict(state_dict)
+    net.generate_style_features(style.to(dev))
+    out = net(frame.to(dev)).cpu().numpy()
+    assert rel_linf(out, gold["out"]) < TOL
+    two = net(torch.cat([frame, frame.flip(3)], 0).to(dev)).cpu().numpy()          # a batch = independent frames
+    assert rel_linf(two[0], gold["out"][0]) < TOL and not np.allclose(two[1], two[0])
+    with pytest.raises(AttributeError):
+        net.add(frame.to(dev))
+
+
+def test_train_model_validation_and_vgg_losses(L, dev, state_dict):
+    """train/style_networks.py on the temporal-loss path (train.py:375-388): validation(), Vgg19 features, calc_mean_std,
+    style_loss, content_loss against the unmodified reference's outputs (tests/golden/train_model.npz)."""
+    from oracle import cases
+    from rerevst_code_b200.style_networks import TransformerNet
+    gold = np.load(os.path.join(GOLDEN, "train_model.npz"))
+    style, frame = cases.frame_inputs("frame_small")
+    net = TransformerNet().to(dev)
+    net.load_state_dict(state_dict)
+    out = net.validation(frame.to(dev), style.to(dev)).cpu().numpy()
+    assert rel_linf(out, gold["validation"]) < TOL
+    g = torch.Generator().manual_seed(4321)
+    other = torch.randn(2, 3, 40, 56, generator=g)
+    fa = net.vgg19(other.to(dev))
+    fb = net.vgg19(torch.flip(other, dims=(0, 3)).to(dev))
+    assert rel_linf(fa.relu4_1.cpu().numpy(), gold["relu4_1"]) < TOL
+    for lvl, ft in zip(fa._fields, fa):
+        mean, std = net.calc_mean_std(ft)
+        assert rel_linf(mean.cpu().numpy(), gold[f"mean/{lvl}"]) < TOL and rel_linf(std.cpu().numpy(), gold[f"std/{lvl}"]) < TOL
+    sl, cl = float(net.style_loss(fa, fb)), float(net.content_loss(fa, fb))
+    assert abs(sl - float(gold["style_loss"])) < 2e-3 * float(gold["style_loss"])
+    assert abs(cl - float(gold["content_loss"])) < 2e-3 * float(gold["content_loss"])
+
+
+def test_stylization_frame_mode_facade(L, dev, state_dict):
+    """framework.Stylization(use_Global=False): transfer() works without add / compute, which raise like the reference."""
+    from oracle import stylenet
+    from rerevst_code_b200.framework import Stylization
+    rng = np.random.RandomState(5)
+    style = rng.randint(0, 256, (48, 56, 3)).astype(np.uint8)
+    frame = rng.randint(0, 256, (40, 64, 3)).astype(np.uint8)
+    fw = Stylization(state_dict, cuda=True, use_Global=False)
+    fw.prepare_style(style)
+    got = fw.transfer(frame)
+    fs = stylenet.encoder_style(stylenet.transform_image(stylenet.numpy2tensor(style)), state_dict)
+    ref = stylenet.frame_mode_forward(state_dict, stylenet.transform_image(stylenet.numpy2tensor(frame)), fs)
+    ref = stylenet.tensor2numpy(stylenet.transform_back_image(ref))
+    assert got.shape == ref.shape and np.abs(got - ref).max() < 255 * TOL * 4
+    with pytest.raises(AttributeError):
+        fw.add(frame)
+
+
 def test_forward_with_oracle_statistics(L, dev, state_dict):
     """Per-frame forward alone: clip state imported from the oracle, so only forward error counts."""
     from oracle import cases, stylenet

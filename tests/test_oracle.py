@@ -55,6 +55,29 @@ def test_frame_mode_matches_golden(name, state_dict):
     assert rel_linf(out.numpy(), gold["out"]) < ORACLE_TOL
 
 
+def test_train_model_matches_golden(state_dict):
+    """train/style_networks.py on the temporal-loss path: validation = frame mode without RGB2Gray,
+    the Vgg19 loss network, calc_mean_std, style_loss and content_loss -- against the unmodified reference's outputs."""
+    gold = np.load(os.path.join(GOLDEN, "train_model.npz"))
+    style, frame = cases.frame_inputs("frame_small")
+    fs = stylenet.encoder_style(style, state_dict)
+    out = stylenet.frame_mode_forward(state_dict, frame, fs, gray=False)
+    assert rel_linf(out.numpy(), gold["validation"]) < ORACLE_TOL
+    g = torch.Generator().manual_seed(4321)
+    other = torch.randn(2, 3, 40, 56, generator=g)
+    fa = stylenet.vgg19_features(other, state_dict)
+    fb = stylenet.vgg19_features(torch.flip(other, dims=(0, 3)), state_dict)
+    assert rel_linf(fa[3].numpy(), gold["relu4_1"]) < ORACLE_TOL
+    sl = 0.0
+    for lvl, a, b in zip(("relu1_1", "relu2_1", "relu3_1", "relu4_1"), fa, fb):
+        ma, mb = stylenet.cal_mean_std(a), stylenet.cal_mean_std(b)
+        assert rel_linf(ma.mean.numpy(), gold[f"mean/{lvl}"]) < ORACLE_TOL and rel_linf(ma.std.numpy(), gold[f"std/{lvl}"]) < ORACLE_TOL
+        sl = sl + torch.nn.functional.mse_loss(ma.mean, mb.mean) + torch.nn.functional.mse_loss(ma.std, mb.std)
+    assert abs(float(sl) - float(gold["style_loss"])) < 1e-5 * abs(float(gold["style_loss"]))
+    cl = torch.nn.functional.mse_loss(fa[3], fb[3])
+    assert abs(float(cl) - float(gold["content_loss"])) < 1e-5 * abs(float(gold["content_loss"]))
+
+
 def test_q1_only_first_sample_is_filtered(state_dict):
     """Quirk Q1: in the pre-pass only sample 0 goes through the dynamic filters and
     its residual is broadcast to every sample."""
