@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <math_constants.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -328,10 +329,13 @@ __device__ __forceinline__ void chain8(const EpiDev& e, const float* s_tab, int 
 // DXM: the accumulator holds the three dx taps side by side (columns [0,Cp) [Cp,2Cp) [2Cp,3Cp), Cp = ts) for INPUT
 // column = lane; output column `lane` = tap0[lane] + tap1[lane+1] + tap2[lane+2] (the lanes of one quadrant are
 // 32 consecutive columns of one image row, the first of them one left of the tile).
-template <int FLAGS, bool DXM>
+// MODE 2 (nearest-x2 convolution, column phases merged): the chunk's two column taps b = 0, 1 sit ts columns apart; lane l is
+// input column x0 - 1 + l and the output column 2 (x0 - 1 + l) + upx is tap0[l - 1] + tap1[l] (upx = 0) or tap0[l] + tap1[l + 1].
+template <int FLAGS, int MODE>
 __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e, const float* s_tab, int ts, uint32_t taddr,
                                                const PixCtx& px, int cb, int col0, int BN, bool pre = false,
-                                               const uint4* pre_rh = nullptr, const uint4* pre_rl = nullptr) {
+                                               const uint4* pre_rh = nullptr, const uint4* pre_rl = nullptr, int upx = 0) {
+    constexpr bool DXM = MODE == 1;
     const bool has_res = FLAGS >= 0 ? (FLAGS & EPI_RES) != 0 : e.res_hi != nullptr;
     // the residual of the whole chunk goes in flight first, ahead of the TMEM loads and the tap combine (volatile loads: the
     // compiler would otherwise sink them to their first use to save registers, and the chain then waits for L2)
@@ -356,7 +360,25 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
         }
     }
     uint32_t r[CW];
-    if (DXM && RRV_EPI_HALF16) {
+    if (MODE == 2) {
+#pragma unroll
+        for (int h = 0; h < CW / 16; ++h) {
+            uint32_t a0[16], a1[16];
+            ptx::tmem_ld16_issue(taddr + (uint32_t)(16 * h), a0);
+            ptx::tmem_ld16_issue(taddr + (uint32_t)(ts + 16 * h), a1);
+            ptx::tmem_ld16_wait(a0);
+            ptx::tmem_ld16_wait(a1);
+            if (upx == 0) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    r[16 * h + i] = __float_as_uint(__shfl_up_sync(0xffffffffu, __uint_as_float(a0[i]), 1) + __uint_as_float(a1[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    r[16 * h + i] = __float_as_uint(__uint_as_float(a0[i]) + __shfl_down_sync(0xffffffffu, __uint_as_float(a1[i]), 1));
+            }
+        }
+    } else if (DXM && RRV_EPI_HALF16) {
 #pragma unroll
         for (int h = 0; h < CW / 16; ++h) {
             uint32_t a0[16], a1[16], a2[16];
@@ -374,7 +396,7 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
                 r[16 * h + i] = __float_as_uint((a + b) + c);
             }
         }
-    } else {
+    } else if (MODE != 2) {
         ptx::tmem_ld32_issue(taddr, r);
     }
     if (DXM && !RRV_EPI_HALF16) {
@@ -392,7 +414,7 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
             r[i] = __float_as_uint((a + b) + c);
         }
     }
-    if (!DXM) ptx::tmem_ld32_wait(r);
+    if (MODE == 0) ptx::tmem_ld32_wait(r);
     if (!px.valid) return;
     if (full && o.out_mode == RRV_OUT_PLANES) {
         // fast path (every per-frame layer but the RGB head): no per-group range checks, planes output
@@ -623,7 +645,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t taddr = tmem_base + (uint32_t)(as * p.acc_stride) + ((uint32_t)(quad * 32) << 16);
             const PixCtx px = make_pix(p.o, e, c.n, oy, ox, valid);
             for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4)
-                epilogue_chunk<FLAGS, false>(p.o, e, s_tab, p.Cout_pad, taddr + (uint32_t)(ch * CW), px, c.n0 + ch * CW, ch * CW, p.BN);
+                epilogue_chunk<FLAGS, 0>(p.o, e, s_tab, p.Cout_pad, taddr + (uint32_t)(ch * CW), px, c.n0 + ch * CW, ch * CW, p.BN);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&s_tempty[as]));
@@ -677,7 +699,13 @@ struct Tc2Params {
     int BN, x3;             // BN = N of the MMA (3 Cout_pad when the dy taps are merged)
     int BNe;                // output channels per tile (= BN, or Cout_pad when merged)
     int b_tile_rows;        // blob rows per weight tile index (Cout_pad, or 3 Cout_pad when merged)
-    int dxm;                // dx taps merged along N: M tile = 4 rows x 32 columns (30 outputs), one TMEM lane quadrant per row
+    int dxm;                // 1: dx taps merged along N: M tile = 4 rows x 32 columns (30 outputs), one TMEM lane quadrant per row
+                            // 2: nearest-x2 convolution with Cout <= 64: the two column phases and their two column taps merged
+                            //    along N (N = 4 Cout_pad = [px0 b0 | px0 b1 | px1 b0 | px1 b1]); nph = 2 row phases are the tiles
+    int dxm_groups;         // weight tiles per A box: 3 (tap rows dy) or 2 (tap rows a of one row phase)
+    int b_parts;            // dxm 2: TMA loads per weight slot and CTA (blocks of Cout_pad blob rows)
+    int tiles_pp;           // dxm 2: tiles per row phase; the row phase is the SLOWEST tile index, so that (b_resident == 2) the
+                            //        2 kchunks weight tiles of a phase are loaded once per phase and worker, not once per tile
     int a_stages, b_slots, b_resident, pair;
     int a_plane_bytes;      // (16 MT + 2) * 1024 (16 MT for 1x1)
     int acc_stride, set_stride, bufs, tmem_cols;
@@ -767,10 +795,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const uint32_t a_plane = (uint32_t)p.a_plane_bytes;
             const bool x3 = p.x3 != 0, resident = p.b_resident != 0, lead = !PAIR || cta_rank == 0;
             const int brow0 = PAIR ? (int)cta_rank * (p.BN / 2) : 0;
+            int prev_ph = -1;
+            uint32_t brel = 0;            // b_resident 2: parity of the "phase drained" completions of s_bempty
             for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
-                int t = tile;
+                const int ph = p.dxm == 2 ? tile / p.tiles_pp : 0;           // dxm 2: the row phase py
+                int t = p.dxm == 2 ? tile % p.tiles_pp : tile;
+                const bool reload = ph != prev_ph;
+                const bool had_phase = prev_ph >= 0;
+                prev_ph = ph;
                 const int bx = ((t % p.tiles_x) * (PAIR ? 2 : 1) + (int)cta_rank) * 30 - 1; t /= p.tiles_x;
-                const int by = (t % p.tiles_y) * 4 - 1;
+                const int by = (t % p.tiles_y) * 4 + (p.dxm == 2 ? ph - 1 : -1);
                 const int n = t / p.tiles_y;
                 for (int kc = 0; kc < kch; ++kc) {
                     ptx::mbar_wait(ptx::smem_u32(&s_aempty[sa]), pa ^ 1u);
@@ -785,12 +819,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         if (x3) ptx::tma_load_4d(dst + a_plane, &map_a_lo, full, kc * BK, bx, by, n);
                     }
                     if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
-                    if (resident && !first_set) continue;
+                    if (p.b_resident == 2 ? !reload : (resident && !first_set)) continue;
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
+                        if (dy >= p.dxm_groups) break;
                         int slot;
                         if (resident) {
                             slot = dy * kch + kc;
+                            if (p.b_resident == 2 && had_phase) ptx::mbar_wait(ptx::smem_u32(&s_bempty[slot]), brel);   // old phase drained
                         } else {
                             slot = sb;
                             ptx::mbar_wait(ptx::smem_u32(&s_bempty[sb]), pb ^ 1u);
@@ -798,8 +834,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         }
                         const uint32_t bfull = ptx::smem_u32(&s_bfull[slot]);
                         const uint32_t bdst = b_base + (uint32_t)slot * b_slot_bytes;
-                        const int brow = dy * p.b_tile_rows + brow0;
                         if (lead) ptx::mbar_expect_tx(bfull, tx_mult * b_slot_bytes);
+                        if (p.dxm == 2) {
+                            // weight tile of (row phase ph, tap row a = dy): blocks (px, b) of Cout_pad rows from the 16-matrix blob
+                            // [(py 2 + px) 4 + a 2 + b]; a pair splits them by column phase (CTA r holds px = r)
+                            for (int q = 0; q < p.b_parts; ++q) {
+                                const int px = PAIR ? (int)cta_rank : (q >> 1), b = q & 1;
+                                const int brow = (((ph * 2 + px) * 4) + dy * 2 + b) * p.Cout_pad;
+                                const uint32_t dq = bdst + (uint32_t)(q * p.Cout_pad) * 128u;
+                                if (PAIR) {
+                                    ptx::tma_load_2d_pair(dq, &map_b_hi, bfull, kc * BK, brow);
+                                    if (x3) ptx::tma_load_2d_pair(dq + b_plane_bytes, &map_b_lo, bfull, kc * BK, brow);
+                                } else {
+                                    ptx::tma_load_2d(dq, &map_b_hi, bfull, kc * BK, brow);
+                                    if (x3) ptx::tma_load_2d(dq + b_plane_bytes, &map_b_lo, bfull, kc * BK, brow);
+                                }
+                            }
+                            continue;
+                        }
+                        const int brow = dy * p.b_tile_rows + brow0;
                         if (PAIR) {
                             ptx::tma_load_2d_pair(bdst, &map_b_hi, bfull, kc * BK, brow);
                             if (x3) ptx::tma_load_2d_pair(bdst + b_plane_bytes, &map_b_lo, bfull, kc * BK, brow);
@@ -810,6 +863,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     }
                 }
                 first_set = false;
+                if (p.b_resident == 2 && reload && had_phase) brel ^= 1u;
             }
         }
     } else if (DXM && warp == 1 && cta_rank == 0) {
@@ -822,7 +876,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const int kch = p.kchunks;
             const uint32_t a_plane = (uint32_t)p.a_plane_bytes;
             const bool x3 = p.x3 != 0, resident = p.b_resident != 0;
+            int prev_ph = -1;
+            uint32_t bfp = 0;             // b_resident 2: parity of this phase's weight loads
             for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
+                const int ph = p.dxm == 2 ? tile / p.tiles_pp : 0;
+                const bool reload = ph != prev_ph;
+                prev_ph = ph;
+                const int nxt = tile + n_workers;
+                const bool last_of_phase = p.b_resident == 2 && (nxt >= p.total_tiles || nxt / p.tiles_pp != ph);
                 ptx::mbar_wait(ptx::smem_u32(&s_tempty[as]), aphase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(as * p.set_stride);
@@ -832,11 +893,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     const uint32_t a_base = smem_base + (uint32_t)sa * a_stage_bytes;
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
+                        if (dy >= p.dxm_groups) break;
                         int slot;
                         if (resident) {
                             slot = dy * kch + kc;
-                            if (first_set) {
-                                ptx::mbar_wait(ptx::smem_u32(&s_bfull[slot]), 0u);
+                            if (p.b_resident == 2 ? reload : first_set) {
+                                ptx::mbar_wait(ptx::smem_u32(&s_bfull[slot]), p.b_resident == 2 ? bfp : 0u);
                                 ptx::tc_fence_after();
                             }
                         } else {
@@ -854,6 +916,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             if (PAIR) ptx::mma_commit_pair(ptx::smem_u32(&s_bempty[sb]));
                             else ptx::mma_commit(ptx::smem_u32(&s_bempty[sb]));
                             if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
+                        } else if (last_of_phase) {          // the producer may overwrite this phase's weights once these MMAs retire
+                            if (PAIR) ptx::mma_commit_pair(ptx::smem_u32(&s_bempty[slot]));
+                            else ptx::mma_commit(ptx::smem_u32(&s_bempty[slot]));
                         }
                     }
                     if (PAIR) {
@@ -866,6 +931,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
                 }
                 first_set = false;
+                if (p.b_resident == 2 && reload) bfp ^= 1u;
                 if (++as == p.bufs) { as = 0; aphase ^= 1u; }
             }
         }
@@ -1006,11 +1072,34 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         uint32_t aphase = 0;
         for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
             int t = tile;
-            const int ph = t % p.nph; t /= p.nph;
+            int ph;
+            if (DXM && p.dxm == 2) { ph = t / p.tiles_pp; t %= p.tiles_pp; }       // row phase slowest
+            else { ph = t % p.nph; t /= p.nph; }
             const int n0 = (t % p.n_ntiles) * p.BNe; t /= p.n_ntiles;
             const int x0 = ((t % p.tiles_x) * (PAIR ? 2 : 1) + (int)cta_rank) * cols_per_tile; t /= p.tiles_x;
             const int y0 = (t % p.tiles_y) * rows_per_set;
             const int n = t / p.tiles_y;
+            if (DXM && p.dxm == 2) {
+                // nearest-x2 convolution, column phases merged: warp (quad, half) = (tile row, column phase px); lanes 1..30 are the
+                // tile's 30 low-resolution columns; output pixel (2 iy + py, 2 ix + px)
+                const int iy = y0 + quad, ix = x0 + lane - 1;
+                const bool valid = lane >= 1 && lane <= 30 && iy < p.in_H && ix < p.in_W;
+                const PixCtx px = make_pix(p.o, e, n, 2 * iy + ph, 2 * ix + half, valid);
+                ptx::mbar_wait(ptx::smem_u32(&s_tfull[as]), aphase);
+                ptx::tc_fence_after();
+                const uint32_t ta = tmem_base + (uint32_t)(as * p.set_stride) + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 2 * p.Cout_pad);
+                for (int c = 0; c < p.Cout_pad / CW; ++c)
+                    epilogue_chunk<FLAGS, 2>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(c * CW), px, c * CW, c * CW, p.Cout_pad, false, nullptr,
+                                             nullptr, half);
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (PAIR) ptx::mbar_arrive_cluster(ptx::smem_u32(&s_tempty[as]), 0u);
+                    else ptx::mbar_arrive(ptx::smem_u32(&s_tempty[as]));
+                }
+                if (++as == p.bufs) { as = 0; aphase ^= 1u; }
+                continue;
+            }
             // the first chunk's output pixel and residual do not depend on the accumulators: fetch them while the MMAs run
             constexpr bool kHasResStatic = FLAGS >= 0 && (FLAGS & EPI_RES) != 0;
             const bool has_res = FLAGS >= 0 ? kHasResStatic : e.res_hi != nullptr;
@@ -1062,7 +1151,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const int ox = p.nph == 4 ? 2 * ix + (ph & 1) : ix;
                 const PixCtx px = make_pix(p.o, e, n, oy, ox, valid);
                 for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4)
-                    epilogue_chunk<FLAGS, DXM>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, ch * CW, p.BNe,
+                    epilogue_chunk<FLAGS, DXM ? 1 : 0>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, ch * CW, p.BNe,
                                                pre && mt == 0 && ch == half, pre_rh, pre_rl);
             }
             ptx::tc_fence_before();
@@ -1276,9 +1365,53 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
 
     int a_stage = 0, b_slot = 0, box_w = 8, box_rows = 0;
     d.dxm = (g_tune.dxm && p->ksize == 3 && !ups && 3 * d.Cout_pad <= 256 && d.in_W >= 16) ? 1 : 0;
+    static const bool no_ups_merge = getenv("RRV_NO_UPS_MERGE") != nullptr;      // A/B switch for measurements
+    if (!no_ups_merge && g_tune.dxm && p->ksize == 3 && ups && 4 * d.Cout_pad <= 256 && d.Cout_pad % CW == 0 && d.in_W >= 16 && p->out_mode == RRV_OUT_PLANES)
+        d.dxm = 2;
     const int xchg_bytes = (p->pool && d.dxm) ? EPI_WARPS * 512 : 0;       // row-partner exchange of the fused max-pool
     const int budget = SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES - xchg_bytes;
-    if (d.dxm) {
+    if (d.dxm == 2) {
+        // ---- nearest-x2 convolution with Cout <= 64 (ResidualBlock slice2.conv1): per output parity the 3x3 convolution is a 2x2
+        //      convolution over the low-resolution input.  With N = Cout = 64 an MMA costs the A fetch (64 cycles) however small N is,
+        //      so the two column phases px and their two column taps b go side by side along N (N = 4 Cout_pad = 256, one A read for
+        //      four weight blocks) and meet in the epilogue through lane shifts, as in the merged 3x3 layers; the two row phases py
+        //      are separate tiles, each with two tap rows a (A box of 5 rows x 32 columns, row a at a 4096-byte offset). ----
+        d.MT = 1;
+        d.nph = 2;
+        d.BN = 4 * d.Cout_pad; d.BNe = d.Cout_pad; d.b_tile_rows = d.Cout_pad;
+        d.n_ntiles = 1;
+        d.pair = (g_tune.pair && num_sms() % 2 == 0) ? 1 : 0;
+        d.a_plane_bytes = 5 * 4096;
+        a_stage = planes * d.a_plane_bytes;
+        b_slot = planes * d.BN * 128 / (d.pair ? 2 : 1);
+        d.acc_stride = d.BN;
+        d.set_stride = d.acc_stride;
+        d.bufs = 2 * d.set_stride <= 512 ? 2 : 1;
+        d.tmem_cols = 32;
+        while (d.tmem_cols < d.bufs * d.set_stride) d.tmem_cols *= 2;
+        if (2 * d.kchunks <= MAX_B_SLOTS && 2 * d.kchunks * b_slot + 2 * a_stage <= budget) {
+            // the weight tiles of one row phase stay in shared memory while a worker walks that phase's tiles (reloading them for
+            // every tile makes the layer L2 -> SM bound: 128 KB of weights against 80 KB of activations per tile)
+            d.b_resident = 2; d.b_slots = 2 * d.kchunks;
+            d.a_stages = std::min(MAX_STAGES, (budget - d.b_slots * b_slot) / a_stage);
+        } else {
+            d.b_resident = 0; d.a_stages = 2; d.b_slots = 2;
+            int rem = budget - 2 * a_stage - 2 * b_slot;
+            RRV_REQUIRE(rem >= 0, "rrv_conv2d(tcgen05 v2): merged-phase tile does not fit shared memory");
+            for (;;) {
+                if (d.b_slots < 4 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
+                if (d.a_stages < 3 && rem >= a_stage) { ++d.a_stages; rem -= a_stage; continue; }
+                break;
+            }
+        }
+        d.dxm_groups = 2;
+        d.b_parts = d.pair ? 2 : 4;
+        d.nA = 1;
+        box_w = 32; box_rows = 5;
+        d.tiles_x = ceil_div(d.in_W, 30 * (d.pair ? 2 : 1));
+        d.tiles_y = ceil_div(d.in_H, 4);
+    } else if (d.dxm) {
+        d.dxm_groups = 3;
         // ---- merged dx taps: N = 3 Cout_pad, M tile = 4 rows x 32 input columns (one TMEM lane quadrant per row).  ONE A box
         //      of 6 rows x 32 columns per chunk serves all nine taps: tap row dy reads it from row dy (a 4096-byte offset, whole
         //      swizzle atoms), the three dx taps are the three column blocks of the weight tile and meet in the epilogue. ----
@@ -1403,6 +1536,7 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     const long long total = (long long)d.N * d.tiles_y * d.tiles_x * d.n_ntiles * d.nph;
     RRV_REQUIRE(total < (1LL << 31), "rrv_conv2d: too many tiles");
     d.total_tiles = (int)total;
+    d.tiles_pp = d.dxm == 2 ? d.total_tiles / d.nph : d.total_tiles;
     d.ep = make_epi(p->ep, p->Cout);
     d.ep.lo_fp16 = 0;
 
@@ -1411,7 +1545,7 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     const uint16_t* w_hi = (const uint16_t*)p->w_tc;
     const uint16_t* w_lo = w_hi + (long long)rows * p->Cin;
     if (encode_act_map(&ma_hi, p->in_hi, d.N, d.in_H, d.in_W, p->Cin, box_w, box_rows)) return 1;
-    const int b_box = d.pair ? d.BN / 2 : d.BN;
+    const int b_box = d.dxm == 2 ? d.Cout_pad : (d.pair ? d.BN / 2 : d.BN);
     if (encode_w_map(&mb_hi, w_hi, rows, p->Cin, b_box)) return 1;
     if (d.x3) {
         if (encode_act_map(&ma_lo, p->in_lo, d.N, d.in_H, d.in_W, p->Cin, box_w, box_rows)) return 1;
@@ -1426,6 +1560,10 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     if (d.dxm) {
         // merged-tap layers: conv1_2 (bias + ReLU [+ pool]), slice2.conv2 (the full chain), the RGB head / anything else (generic)
         const int f = (flags == 0 || flags == (EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF)) ? flags : -1;
+        if (flags == EPI_N1) {          // slice2.conv1 (merged column phases)
+            if (d.pair) return launch_tc2p<EPI_N1, true, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+            return launch_tc2p<EPI_N1, false, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        }
         if (d.pair) {
             if (f == 0) return launch_tc2p<0, true, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
             if (f > 0) return launch_tc2p<EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF, true, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
