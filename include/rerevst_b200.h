@@ -56,6 +56,8 @@ typedef struct rrv_epilogue {
     int64_t      res_batch_stride; /* elements; 0 broadcasts one residual over the batch */
     const float* norm2;     /* [4][C] or NULL */
     const float* affine;    /* [2][C] or NULL */
+    int32_t      res_f32;   /* 1: res_hi points to an fp32 NHWC tensor (res_lo NULL): the 1x1 shortcut of a ResidualBlock is
+                             * kept in fp32 -- the same bytes as two 16-bit planes, one add instead of unpack + two */
 } rrv_epilogue;
 
 enum { RRV_OUT_PLANES = 0, RRV_OUT_F32_NHWC = 1, RRV_OUT_F32_NCHW = 2 };

@@ -22,7 +22,7 @@ class Epilogue(C.Structure):
     """``rrv_epilogue`` (include/rerevst_b200.h)."""
     _fields_ = [("bias", _vp), ("act", _i32), ("norm1", _vp), ("res_hi", _vp), ("res_lo", _vp),
                 ("res_shift", _i32), ("res_H", _i32), ("res_W", _i32), ("res_batch_stride", _i64),
-                ("norm2", _vp), ("affine", _vp)]
+                ("norm2", _vp), ("affine", _vp), ("res_f32", _i32)]
 
 
 class Conv(C.Structure):

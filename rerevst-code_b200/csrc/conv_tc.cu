@@ -267,7 +267,10 @@ __device__ __forceinline__ void chain8(const EpiDev& e, const float* s_tab, int 
         for (int i = 0; i < 8; ++i) x[i] = fminf(k1[i], fmaxf(k0[i], x[i]));
     }
     if (has_res) {
-        if (res_packed) {
+        if (res_packed && e.res_f32) {        // fp32 residual: rh = channels 0..3, rl = channels 4..7
+            x[0] += __uint_as_float(rh.x); x[1] += __uint_as_float(rh.y); x[2] += __uint_as_float(rh.z); x[3] += __uint_as_float(rh.w);
+            x[4] += __uint_as_float(rl.x); x[5] += __uint_as_float(rl.y); x[6] += __uint_as_float(rl.z); x[7] += __uint_as_float(rl.w);
+        } else if (res_packed) {
             const uint32_t hw[4] = {rh.x, rh.y, rh.z, rh.w};
             const uint32_t lw[4] = {rl.x, rl.y, rl.z, rl.w};
 #pragma unroll
@@ -284,7 +287,8 @@ __device__ __forceinline__ void chain8(const EpiDev& e, const float* s_tab, int 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int cc = c0 + i;
-                float rr = cc < Cout ? bf16_to_f32(e.res_hi[px.res_off + cc]) : 0.0f;
+                float rr = 0.0f;
+                if (cc < Cout) rr = e.res_f32 ? reinterpret_cast<const float*>(e.res_hi)[px.res_off + cc] : bf16_to_f32(e.res_hi[px.res_off + cc]);
                 if (res_x3 && cc < Cout) rr += bf16_to_f32(e.res_lo[px.res_off + cc]);
                 x[i] += rr;
             }
@@ -351,8 +355,14 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
 #pragma unroll
         for (int g = 0; g < CW / 8; ++g) {
 #if RRV_EPI_RESVOL
-            rh[g] = ptx::ldg_nc_v4(e.res_hi + px.res_off + cb + g * 8);
-            if (e.res_lo) rl[g] = ptx::ldg_nc_v4(e.res_lo + px.res_off + cb + g * 8);
+            if (e.res_f32) {
+                const float* rf = reinterpret_cast<const float*>(e.res_hi) + px.res_off + cb + g * 8;
+                rh[g] = ptx::ldg_nc_v4(rf);
+                rl[g] = ptx::ldg_nc_v4(rf + 4);
+            } else {
+                rh[g] = ptx::ldg_nc_v4(e.res_hi + px.res_off + cb + g * 8);
+                if (e.res_lo) rl[g] = ptx::ldg_nc_v4(e.res_lo + px.res_off + cb + g * 8);
+            }
 #else
             rh[g] = *reinterpret_cast<const uint4*>(e.res_hi + px.res_off + cb + g * 8);
             if (e.res_lo) rl[g] = *reinterpret_cast<const uint4*>(e.res_lo + px.res_off + cb + g * 8);
@@ -730,6 +740,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         s_tfull[2], s_tempty[2];
     __shared__ uint32_t s_tmem_base;
 
+    // Programmatic dependent launch: the next convolution of the frame may be scheduled as soon as SMs free up, so that its
+    // prologue (barrier init, TMEM allocation, constants table, descriptor prefetch) overlaps this kernel's tail; it reads
+    // and writes activations only after its own griddepcontrol.wait below, i.e. after this whole grid has completed.
+    ptx::pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t planes = p.x3 ? 2u : 1u;
@@ -781,6 +795,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     if (PAIR) ptx::cluster_sync();          // the peer's barriers are initialised before anyone signals them
     else __syncthreads();
     ptx::tc_fence_after();
+    ptx::pdl_wait();                        // everything above ran while the previous kernel was still finishing
     const uint32_t tmem_base = s_tmem_base;
     const int rows_per_set = DXM ? 4 : 16 * p.MT;
     const int cols_per_tile = DXM ? 30 : 8;                  // merged taps: 32 input columns give 30 output columns
@@ -1113,7 +1128,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const PixCtx px = make_pix(p.o, e, n, oy, ox, valid);
                 const int cb = n0 + half * CW;
                 const bool can = half < nchunks && cb + CW <= p.o.Cout && half * CW + CW <= p.BNe;      // warp-uniform
-                if (RRV_EPI_PREFETCH == 1) {
+                if (RRV_EPI_PREFETCH == 1 && !e.res_f32) {
                     pre = can;
                     if (pre && valid) {
 #pragma unroll
@@ -1123,8 +1138,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         }
                     }
                 } else if (can && valid) {                 // CW channels = 64 bytes = half a line per plane
-                    ptx::prefetch_l1(e.res_hi + px.res_off + cb);
-                    if (e.res_lo) ptx::prefetch_l1(e.res_lo + px.res_off + cb);
+                    if (e.res_f32) {
+                        ptx::prefetch_l1(reinterpret_cast<const float*>(e.res_hi) + px.res_off + cb);
+                    } else {
+                        ptx::prefetch_l1(e.res_hi + px.res_off + cb);
+                        if (e.res_lo) ptx::prefetch_l1(e.res_lo + px.res_off + cb);
+                    }
                 }
             }
             ptx::mbar_wait(ptx::smem_u32(&s_tfull[as]), aphase);
@@ -1313,24 +1332,30 @@ int launch_tc2p(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, c
         RRV_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(conv_tc2_kernel): %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    if (!PAIR) {
-        conv_tc2_kernel<FLAGS, PAIR, DXM><<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, d);
-    } else {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid);
-        cfg.blockDim = dim3(TC_THREADS);
-        cfg.dynamicSmemBytes = (size_t)smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<FLAGS, PAIR, DXM>, ma_hi, ma_lo, mb_hi, mb_lo, d);
-        RRV_REQUIRE(e == cudaSuccess, "cudaLaunchKernelEx(conv_tc2_kernel, cluster 2): %s", cudaGetErrorString(e));
+    static const bool no_pdl = getenv("RRV_NO_PDL") != nullptr;          // A/B switch for measurements
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (PAIR) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
     }
+    if (!no_pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<FLAGS, PAIR, DXM>, ma_hi, ma_lo, mb_hi, mb_lo, d);
+    RRV_REQUIRE(e == cudaSuccess, "cudaLaunchKernelEx(conv_tc2_kernel%s): %s", PAIR ? ", cluster 2" : "", cudaGetErrorString(e));
     return check_launch("conv_tc2_kernel");
 }
 

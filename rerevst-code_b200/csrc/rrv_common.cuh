@@ -85,7 +85,7 @@ struct EpiDev {
     const float* norm2;
     const float* affine;
     long long res_batch_stride;
-    int act, res_shift, res_H, res_W, C, lo_fp16;
+    int act, res_shift, res_H, res_W, C, lo_fp16, res_f32;
 };
 
 inline EpiDev make_epi(const rrv_epilogue& e, int C) {
@@ -103,6 +103,7 @@ inline EpiDev make_epi(const rrv_epilogue& e, int C) {
     d.res_W = e.res_W;
     d.C = C;
     d.lo_fp16 = g_lo_fp16;
+    d.res_f32 = e.res_f32;
     return d;
 }
 
@@ -135,7 +136,11 @@ __device__ __forceinline__ void apply_epilogue(const EpiDev& e, float* v, int n,
     if (e.res_hi != nullptr) {
         const long long off = (long long)n * e.res_batch_stride +
                               ((long long)(y >> e.res_shift) * e.res_W + (x >> e.res_shift)) * e.C + c0;
-        if (NV == 8) {
+        if (e.res_f32) {
+            const float* rf = reinterpret_cast<const float*>(e.res_hi) + off;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) v[i] += __ldg(rf + i);
+        } else if (NV == 8) {
             float r[8];
             load8(e.res_hi + off, e.res_lo ? e.res_lo + off : nullptr, e.lo_fp16, r);
 #pragma unroll

@@ -70,6 +70,10 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+// ---- programmatic dependent launch ----------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- TMA -------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");

@@ -85,7 +85,11 @@ def make_epilogue(bias=None, act=0, norm1=None, res=None, res_shift=0, res_broad
     e.bias = L.ptr(bias)
     e.act = act
     e.norm1 = L.ptr(norm1)
-    if res is not None:
+    if isinstance(res, torch.Tensor):            # fp32 NHWC residual (the 1x1 shortcut of a ResidualBlock)
+        e.res_hi, e.res_lo, e.res_f32 = res.data_ptr(), 0, 1
+        e.res_shift, e.res_H, e.res_W = res_shift, res.shape[1], res.shape[2]
+        e.res_batch_stride = 0 if res_broadcast else res.shape[1] * res.shape[2] * res.shape[3]
+    elif res is not None:
         e.res_hi, e.res_lo = L.ptr(res.hi), L.ptr(res.lo)
         e.res_shift, e.res_H, e.res_W = res_shift, res.H, res.W
         e.res_batch_stride = 0 if res_broadcast else res.H * res.W * res.C
@@ -445,7 +449,7 @@ class StyleEngine:
                 h = self._conv(up, t, make_epilogue(bias=up.bias, res=h, norm2=st["norm1"], affine=tabs["relu4_1"]))
         for block, nxt, lvl in (("slice4", "norm2", "relu3_1"), ("slice3", "norm3", "relu2_1"), ("slice2", "norm4", "relu1_1")):
             bw = self.w[block]
-            s = self._conv(bw["short"], h, make_epilogue())                 # 1x1 shortcut at low resolution
+            s = self._conv(bw["short"], h, make_epilogue(), L.OUT_F32_NHWC)   # 1x1 shortcut at low resolution, kept in fp32
             y = self._conv(bw["conv1"], h, make_epilogue(bias=bw["conv1"].bias, act=2, norm1=st[block + ".norm1"]))
             h = self._conv(bw["conv2"], y, make_epilogue(bias=bw["conv2"].bias, act=2, norm1=st[block + ".norm2"],
                                                         res=s, res_shift=1, norm2=st[nxt], affine=tabs[lvl]))

@@ -195,17 +195,19 @@ def test_conv_full_epilogue_chain(L, dev):
     cw = ConvW(w.to(dev), b.to(dev))
     xp, rp = _to_planes(L, x.to(dev)), _to_planes(L, res.to(dev))
     t1, t2, aff = tab(st1), tab(st2), torch.stack([sc, sh]).contiguous().to(dev)
+    rf = res.permute(0, 2, 3, 1).contiguous().to(dev)            # the same residual as an fp32 NHWC tensor (rrv_epilogue.res_f32)
     for name, impl in _impls(L):
-        d = L.Conv()
-        d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = N, H, W, Cc, Cc, 3, 0
-        d.in_hi, d.in_lo = L.ptr(xp.hi), L.ptr(xp.lo)
-        d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
-        d.ep = make_epilogue(bias=cw.bias, act=2, norm1=t1, res=rp, res_shift=1, norm2=t2, affine=aff)
-        from rerevst_code_b200.engine import Planes
-        o = Planes(N, H, W, Cc, True, dev)
-        d.out_mode, d.out_hi, d.out_lo = L.OUT_PLANES, L.ptr(o.hi), L.ptr(o.lo)
-        L.check(L.lib().rrv_conv2d(C.byref(d), impl, L.stream()), name)
-        assert rel_linf(_from_planes(L, o).cpu(), ref) < 3e-4, name
+        for residual in (rp, rf):
+            d = L.Conv()
+            d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = N, H, W, Cc, Cc, 3, 0
+            d.in_hi, d.in_lo = L.ptr(xp.hi), L.ptr(xp.lo)
+            d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
+            d.ep = make_epilogue(bias=cw.bias, act=2, norm1=t1, res=residual, res_shift=1, norm2=t2, affine=aff)
+            from rerevst_code_b200.engine import Planes
+            o = Planes(N, H, W, Cc, True, dev)
+            d.out_mode, d.out_hi, d.out_lo = L.OUT_PLANES, L.ptr(o.hi), L.ptr(o.lo)
+            L.check(L.lib().rrv_conv2d(C.byref(d), impl, L.stream()), name)
+            assert rel_linf(_from_planes(L, o).cpu(), ref) < 3e-4, (name, residual is rf)
 
 
 @pytest.mark.parametrize("kind,gray", [(0, 1), (0, 0), (1, 1), (1, 0)])
