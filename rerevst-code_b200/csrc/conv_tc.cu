@@ -1475,8 +1475,15 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     } else {
         // ---- tile shape: Cout tile BN, M tiles per weight tile MT ----
         int BN = std::min(d.Cout_pad, g_tune.max_bn);
-        while (BN > 16 && d.Cout_pad % BN != 0) BN -= 16;
         int MT = std::max(1, std::min(g_tune.mt, 2));
+        // few MMAs per output value (the 1x1 shortcuts, the KernelFilter up-convolutions): the epilogue is the kernel's time and
+        // nothing is gained from sharing a weight tile between two M tiles; smaller work items balance the 148 SMs better
+        const int k_real = (ups ? 4 : p->ksize * p->ksize) * (p->Cin_used > 0 ? p->Cin_used : p->Cin);
+        if (k_real < 576 && g_tune.mt == 2 && g_tune.max_bn == 256) {
+            MT = 1;
+            BN = std::min(BN, 128);
+        }
+        while (BN > 16 && d.Cout_pad % BN != 0) BN -= 16;
         if (d.in_H <= 16) MT = 1;
         // all weight tiles resident beats sharing them between two M tiles: prefer MT = 1 if that is what fits
         const bool resident_shape = !ups && BN == d.Cout_pad && btiles * d.kchunks <= MAX_B_SLOTS;

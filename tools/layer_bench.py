@@ -16,6 +16,7 @@ LAYERS = {  # name: (H, W, Cin, Cout, k, ups)
     "c256_256": (304, 512, 256, 256, 3, 0), "c256_512": (152, 256, 256, 512, 3, 0), "c512_64": (152, 256, 512, 64, 3, 0),
     "c64_512": (152, 256, 64, 512, 3, 0), "u512_256": (304, 512, 512, 256, 3, 1), "u256_128": (608, 1024, 256, 128, 3, 1),
     "u128_64": (1216, 2048, 128, 64, 3, 1), "s128_64": (608, 1024, 128, 64, 1, 0), "head": (1216, 2048, 64, 3, 3, 0),
+    "s512_256": (152, 256, 512, 256, 1, 0), "s256_128": (304, 512, 256, 128, 1, 0),
 }
 
 
@@ -72,6 +73,12 @@ def bench(name, tunings, iters=5):
 
 
 if __name__ == "__main__":
+    if "--small" in sys.argv:
+        T = {"default": (2, 2, 0, 1, 64, 256), "mt1": (2, 1, 0, 1, 64, 256), "bn128": (2, 2, 0, 1, 64, 128), "mt1_bn128": (2, 1, 0, 1, 64, 128),
+             "mt1_bn64": (2, 1, 0, 1, 64, 64)}
+        for n in [a for a in sys.argv[1:] if not a.startswith("--")]:
+            bench(n, T, iters=20)
+        sys.exit(0)
     T = {"default": (2, 2, 0, 1, 64, 256), "nomerge": (2, 2, 0, 1, 64, 256, 0), "nopair": (2, 2, 0, 0, 64, 256),
          "nopair_nomerge": (2, 2, 0, 0, 64, 256, 0), "v1": (1, 2, 1, 0, 128, 256), "pair32": (2, 2, 0, 1, 32, 256)}
     names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(LAYERS)
