@@ -152,6 +152,13 @@ constexpr int FL_TPB = 4;      // consecutive tiles (along x) per block: the wei
 
 __device__ __forceinline__ float gray_u(const FirstDev& p, int n, int y, int x) {
     if (y < 0 || y >= p.H || x < 0 || x >= p.W) return 0.0f;
+    if (p.src_kind == 1) {
+        // uint8 BGR: normalise -> de-normalise -> gray collapses to gray = (0.299 B + 0.587 G + 0.114 R) / 255 (the reference
+        // applies the BGR weights to its RGB tensor: ch2 = B); the reference's six divisions only add rounding noise of 1e-7
+        const uint8_t* s = (const uint8_t*)p.src + (((long long)n * p.H + y) * p.W + x) * 3;
+        const float g = fmaf(0.114f, (float)s[2], fmaf(0.587f, (float)s[1], 0.299f * (float)s[0])) * (1.0f / 255.0f);
+        return (g - GRAY_GM) * (1.0f / GRAY_GS);
+    }
     float v[3];
     load_normalised(p, n, y, x, v);
     return (gray_value(v) - GRAY_GM) * (1.0f / GRAY_GS);

@@ -64,6 +64,20 @@ __device__ __forceinline__ void load8(const uint16_t* hi, const uint16_t* lo, in
 
 __device__ __forceinline__ void store8(uint16_t* hi, uint16_t* lo, int lo_fp16, const float* v) {
     uint32_t hw[4], lw[4];
+    if (!lo_fp16) {                      // bf16 lo (the default): two values per conversion instruction
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+            const float r0 = v[2 * i] - __uint_as_float(hw[i] << 16);
+            const float r1 = v[2 * i + 1] - __uint_as_float(hw[i] & 0xffff0000u);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(r0, r1);
+            lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+        }
+        *reinterpret_cast<uint4*>(hi) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        if (lo != nullptr) *reinterpret_cast<uint4*>(lo) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         uint16_t h0, l0, h1, l1;

@@ -384,6 +384,39 @@ def test_stylization_frame_mode_facade(L, dev, state_dict):
         fw.add(frame)
 
 
+def test_full_size_raw_1080p_against_oracle(L, dev, state_dict):
+    """BASELINE's full frame size WITHOUT the script's padding: 1080x1920 is 135x240 at 1/8 scale -- no multiple of any tile
+    (ragged row tiles at every level, the fused max-pools next to image edges).  The CPU oracle takes the clip statistics
+    from the GPU pre-pass, so the comparison isolates the per-frame forward; ~4 s of CPU time."""
+    import bench
+    from oracle import stylenet
+    from rerevst_code_b200.framework import Stylization
+    fw = Stylization(state_dict, cuda=True)
+    fw.prepare_style(bench.synthetic_frame(256, 320, 1))
+    fw.clean()
+    for i in range(2):
+        fw.add(bench.synthetic_frame(270, 480, 50 + i))
+    fw.compute()
+    eng = fw.model._eng()
+    frame = bench.synthetic_frame(1080, 1920, 100)
+    got = eng.forward(torch.from_numpy(frame).unsqueeze(0).to(dev), kind=1).cpu()
+    o = stylenet.GlobalOracle(state_dict)
+    st = eng.export_clip_state()
+    clip = stylenet.ClipState()
+    for k, v in st["stats"].items():
+        t = v.cpu()
+        clip.stats[k] = stylenet.SavedStat(*[t[i].view(1, -1, 1, 1) for i in range(4)])
+    for k, (a, b) in st["filters"].items():
+        clip.filters[k] = (a.cpu().view(1, 32, 32), b.cpu().view(1, 32, 32))
+    o.clip = clip
+    ms_ = {k: stylenet.MeanStd(v[1].cpu().view(1, -1, 1, 1), v[0].cpu().view(1, -1, 1, 1)) for k, v in eng.style["tabs"].items()}
+    o.F_style = stylenet.StyleFeatures(None, ms_["relu1_1"], ms_["relu2_1"], ms_["relu3_1"], ms_["relu4_1"])
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref = o.forward(stylenet.transform_image(stylenet.numpy2tensor(frame)))
+    assert tuple(got.shape) == (1, 3, 1080, 1920)
+    assert rel_linf(got.numpy(), ref.numpy()) < TOL
+
+
 def test_forward_with_oracle_statistics(L, dev, state_dict):
     """Per-frame forward alone: clip state imported from the oracle, so only forward error counts."""
     from oracle import cases, stylenet
