@@ -139,6 +139,9 @@ int rrv_pointwise(const float* in, int64_t in_batch_stride, int N, int H, int W,
 /* planes -> fp32 NCHW (debug / feature export) and fp32 NCHW -> planes. */
 int rrv_planes_to_nchw(const void* hi, const void* lo, int N, int H, int W, int C, float* out, void* stream);
 int rrv_nchw_to_planes(const float* in, int N, int H, int W, int C, void* hi, void* lo, void* stream);
+/* ReshapeTool.process (test/generate_real_video.py:66-83): cv2.copyMakeBorder(..., BORDER_REFLECT) of uint8 HWC frames on
+ * the device, [N][H][W][3] -> [N][PH][PW][3] with the image at (top, left); the edge pixel is repeated. */
+int rrv_reflect_pad_u8(const void* src, int N, int H, int W, int top, int left, int PH, int PW, void* dst, void* stream);
 /* transform_back_image + tensor2numpy (test/framework.py:39-49): fp32 NCHW [N][3][H][W] ->
  * fp32 HWC BGR in [0,255], cropped to rows [y0, y0+h) and cols [x0, x0+w)
  * (generate_real_video.py:167). */

@@ -54,6 +54,7 @@ SIGNATURES = {
                                 _vp, _vp, _vp, _vp]),
     "rrv_planes_to_nchw": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rrv_nchw_to_planes": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "rrv_reflect_pad_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rrv_postprocess_bgr": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rrv_channel_stats": (C.c_int, [_vp, _i64, C.c_int, _vp, _vp]),
     "rrv_stats_merge": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),

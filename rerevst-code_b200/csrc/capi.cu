@@ -38,6 +38,7 @@ int tc_tune_pair(int enable, int min_bn);
 int tc_tune_merge(int enable);
 int first_layer(const void* src, int src_kind, int gray, int N, int H, int W, const float* w, const float* bias,
                 void* out_hi, void* out_lo, float* out_f32, cudaStream_t st);
+int reflect_pad_u8(const void* src, int N, int H, int W, int top, int left, int PH, int PW, void* dst, cudaStream_t st);
 int maxpool2x2(const void* in_hi, const void* in_lo, int N, int H, int W, int C, void* out_hi, void* out_lo, cudaStream_t st);
 int pointwise(const float* in, long long in_bs, int N, int H, int W, int C, const rrv_epilogue* ep, int out_mode,
               void* out_hi, void* out_lo, float* out_f32, cudaStream_t st);
@@ -92,6 +93,9 @@ int rrv_pack_weights_f32(const float* w, int Cin, int Cout, int ksize, int Cin_p
 int rrv_first_layer(const void* src, int src_kind, int gray, int N, int H, int W, const float* w, const float* bias,
                     void* out_hi, void* out_lo, float* out_f32, void* stream) {
     return first_layer(src, src_kind, gray, N, H, W, w, bias, out_hi, out_lo, out_f32, ST(stream));
+}
+int rrv_reflect_pad_u8(const void* src, int N, int H, int W, int top, int left, int PH, int PW, void* dst, void* stream) {
+    return reflect_pad_u8(src, N, H, W, top, left, PH, PW, dst, ST(stream));
 }
 int rrv_maxpool2x2(const void* in_hi, const void* in_lo, int N, int H, int W, int C, void* out_hi, void* out_lo, void* stream) {
     return maxpool2x2(in_hi, in_lo, N, H, W, C, out_hi, out_lo, ST(stream));

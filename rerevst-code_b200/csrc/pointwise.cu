@@ -172,6 +172,39 @@ __global__ void __launch_bounds__(256) postprocess_kernel(const float* __restric
     }
 }
 
+// cv2.copyMakeBorder(img, top, bottom, left, right, BORDER_REFLECT) of generate_real_video.py:80-82 on the device: the edge pixel
+// is repeated (fedcba|abcdefgh|hgfedcb), borders wider than the image keep reflecting.
+__device__ __forceinline__ int reflect_index(int i, int n) {
+    const int period = 2 * n;
+    i %= period;
+    if (i < 0) i += period;
+    return i < n ? i : period - 1 - i;
+}
+
+__global__ void __launch_bounds__(256) reflect_pad_kernel(const uint8_t* __restrict__ src, int N, int H, int W, int top, int left,
+                                                          int PH, int PW, uint8_t* __restrict__ dst) {
+    const long long total = (long long)N * PH * PW;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int x = (int)(i % PW);
+        long long t = i / PW;
+        const int y = (int)(t % PH);
+        const int n = (int)(t / PH);
+        const uint8_t* s = src + (((long long)n * H + reflect_index(y - top, H)) * W + reflect_index(x - left, W)) * 3;
+        uint8_t* d = dst + i * 3;
+        d[0] = s[0]; d[1] = s[1]; d[2] = s[2];
+    }
+}
+
+int reflect_pad_u8(const void* src, int N, int H, int W, int top, int left, int PH, int PW, void* dst, cudaStream_t st) {
+    RRV_REQUIRE(src && dst, "rrv_reflect_pad_u8: NULL tensor");
+    RRV_REQUIRE(N > 0 && H > 0 && W > 0 && top >= 0 && left >= 0 && PH >= top + H && PW >= left + W,
+                "rrv_reflect_pad_u8: the padded size %dx%d does not contain the %dx%d image at (%d, %d)", PH, PW, H, W, top, left);
+    const long long total = (long long)N * PH * PW;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+    reflect_pad_kernel<<<grid, 256, 0, st>>>((const uint8_t*)src, N, H, W, top, left, PH, PW, (uint8_t*)dst);
+    return check_launch("reflect_pad_kernel");
+}
+
 int postprocess_bgr(const float* in, int N, int H, int W, int y0, int x0, int h, int w, float* out, cudaStream_t st) {
     RRV_REQUIRE(in && out, "rrv_postprocess_bgr: NULL tensor");
     RRV_REQUIRE(y0 >= 0 && x0 >= 0 && y0 + h <= H && x0 + w <= W, "rrv_postprocess_bgr: crop outside the image");

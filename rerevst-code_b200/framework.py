@@ -76,11 +76,14 @@ class Stylization:
         out = self.transfer_device(frame, crop)
         return out.cpu().numpy()[0]
 
-    def transfer_stream(self, frames, crop=None, depth=3):
+    def transfer_stream(self, frames, crop=None, depth=3, pad_to=None):
         """Generator over an iterable of uint8 BGR frames of one size: yields exactly what
         ``transfer(frame, crop)`` returns for each, in order, but pipelined -- the pinned-memory
         upload of frame i+1 (copy-in stream) and the download of frame i-1 (copy-out stream) overlap the
-        kernels of frame i (current stream).  ``depth`` frames are in flight."""
+        kernels of frame i (current stream).  ``depth`` frames are in flight.
+
+        ``pad_to=(PH, PW)``: the frames are RAW; ReshapeTool.process (generate_real_video.py:66-83, reflect border of 64
+        pixels up to PH x PW) runs on the device, and ``crop`` defaults to the raw frame's window (:167)."""
         eng = self.model._eng()
         cur = torch.cuda.current_stream(self.device)
         s_in, s_out = self._side_streams()
@@ -94,11 +97,19 @@ class Stylization:
             frame = np.ascontiguousarray(frame)
             if frame.dtype != np.uint8 or frame.ndim != 3 or frame.shape[2] != 3:
                 raise ValueError("expected a uint8 HxWx3 BGR image (cv2.imread layout)")
-            H, W = frame.shape[:2]
-            y0, x0, h, w = crop if crop is not None else (0, 0, H, W)
+            rH, rW = frame.shape[:2]                       # as uploaded
+            H, W = pad_to if pad_to is not None else (rH, rW)      # as seen by the network
+            if crop is not None:
+                y0, x0, h, w = crop
+            elif pad_to is not None:
+                y0, x0, h, w = 64, 64, rH, rW
+            else:
+                y0, x0, h, w = 0, 0, H, W
             if len(slots) < depth:
-                slots.append(dict(host_in=torch.empty((1, H, W, 3), dtype=torch.uint8).pin_memory(),
-                                  dev_in=torch.empty((1, H, W, 3), dtype=torch.uint8, device=self.device),
+                slots.append(dict(host_in=torch.empty((1, rH, rW, 3), dtype=torch.uint8).pin_memory(),
+                                  dev_in=torch.empty((1, rH, rW, 3), dtype=torch.uint8, device=self.device),
+                                  dev_pad=(torch.empty((1, H, W, 3), dtype=torch.uint8, device=self.device)
+                                           if pad_to is not None else None),
                                   dev_out=torch.empty((1, h, w, 3), dtype=torch.float32, device=self.device),
                                   host_out=torch.empty((1, h, w, 3), dtype=torch.float32).pin_memory(),
                                   ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(),
@@ -106,7 +117,7 @@ class Stylization:
             slot = slots[i % depth]
             if len(pending) == depth:                       # this slot's previous frame must be handed out first
                 yield finish(pending.pop(0))
-            if tuple(slot["host_in"].shape[1:3]) != (H, W):
+            if tuple(slot["host_in"].shape[1:3]) != (rH, rW):
                 raise ValueError("transfer_stream needs frames of one size")
             slot["host_in"][0].copy_(torch.from_numpy(frame))
             with torch.cuda.stream(s_in):
@@ -115,7 +126,12 @@ class Stylization:
                 slot["ev_in"].record(s_in)
             cur.wait_event(slot["ev_in"])
             cur.wait_event(slot["ev_out"])                  # dev_out of this slot has been downloaded
-            net_out = self._net(eng, slot["dev_in"])
+            net_in = slot["dev_in"]
+            if pad_to is not None:
+                net_in = slot["dev_pad"]
+                L.check(L.lib().rrv_reflect_pad_u8(slot["dev_in"].data_ptr(), 1, rH, rW, 64, 64, H, W, net_in.data_ptr(), L.stream()),
+                        "rrv_reflect_pad_u8")
+            net_out = self._net(eng, net_in)
             L.check(L.lib().rrv_postprocess_bgr(net_out.data_ptr(), 1, H, W, y0, x0, h, w, slot["dev_out"].data_ptr(),
                                                 L.stream()), "rrv_postprocess_bgr")
             slot["ev_free"].record(cur)

@@ -81,18 +81,11 @@ def main(style_img="./inputs/plum_flower.jpg", content_video="./inputs/ambush_4/
         framework.compute()
         say("Preparations finish!")
 
-    reshape = ReshapeTool()
-    shapes = []
-
-    def padded_frames():
-        for i in range(frame_num):
-            img = cv2.imread(frame_list[i])
-            shapes.append(img.shape)
-            yield reshape.process(img)
-
+    # ReshapeTool.process (:66-83) runs on the device: the raw frame is uploaded and reflect-padded there (rrv_reflect_pad_u8)
     first = cv2.imread(frame_list[0]) if frame_num else None
-    crop = (64, 64, first.shape[0], first.shape[1]) if first is not None else None
-    for i, styled in enumerate(framework.transfer_stream(padded_frames(), crop=crop)):
+    pad_to = padded_size(first.shape[0], first.shape[1]) if first is not None else None
+    raw_frames = (cv2.imread(frame_list[i]) for i in range(frame_num))
+    for i, styled in enumerate(framework.transfer_stream(raw_frames, pad_to=pad_to)):
         say("Stylizing frame %d" % i)
         cv2.imwrite(os.path.join(out_dir, os.path.basename(frame_list[i])), styled)
 

@@ -610,6 +610,24 @@ def test_conv_fused_maxpool(L, dev, case, pair, merge):
         L.check(L.lib().rrv_tc_tune_merge(1))
 
 
+def test_reflect_pad_matches_copy_make_border(L, dev):
+    """rrv_reflect_pad_u8 = cv2.copyMakeBorder(..., BORDER_REFLECT) of ReshapeTool.process (edge pixel repeated), including
+    borders wider than the image; transfer_stream(pad_to=...) equals padding on the host."""
+    rng = np.random.RandomState(9)
+    for (h, w, ph, pw) in ((40, 56, 192, 192), (3, 5, 192, 256), (1080, 1920, 1216, 2048)):
+        img = rng.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        ref = np.pad(img, ((64, ph - 64 - h), (64, pw - 64 - w), (0, 0)), mode="symmetric")
+        try:
+            import cv2
+            assert np.array_equal(ref, cv2.copyMakeBorder(img, 64, ph - 64 - h, 64, pw - 64 - w, cv2.BORDER_REFLECT))
+        except ImportError:
+            pass
+        src = torch.from_numpy(img).unsqueeze(0).to(dev)
+        dst = torch.empty((1, ph, pw, 3), dtype=torch.uint8, device=dev)
+        L.check(L.lib().rrv_reflect_pad_u8(src.data_ptr(), 1, h, w, 64, 64, ph, pw, dst.data_ptr(), L.stream()))
+        assert np.array_equal(dst[0].cpu().numpy(), ref), (h, w)
+
+
 def test_transfer_stream_equals_transfer(L, dev, state_dict):
     from rerevst_code_b200.framework import Stylization
     rng = np.random.RandomState(5)
@@ -626,6 +644,13 @@ def test_transfer_stream_equals_transfer(L, dev, state_dict):
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
+    # pad_to: raw frames, reflect border on the device, cropped back to the raw window (generate_real_video.py:66-83, :167)
+    raw = [smooth(40, 56) for _ in range(4)]
+    padded = [np.pad(f, ((64, 192 - 64 - 40), (64, 192 - 64 - 56), (0, 0)), mode="symmetric") for f in raw]
+    want = [fw.transfer(f, crop=(64, 64, 40, 56)) for f in padded]
+    got = list(fw.transfer_stream(iter(raw), pad_to=(192, 192)))
+    for a, b in zip(got, want):
+        assert a.shape == (40, 56, 3) and np.array_equal(a, b)
 
 
 def test_generate_real_video_entry(tmp_path, dev, state_dict):
