@@ -76,11 +76,15 @@ class Stylization:
         out = self.transfer_device(frame, crop)
         return out.cpu().numpy()[0]
 
-    def transfer_stream(self, frames, crop=None, depth=3, pad_to=None):
+    def transfer_stream(self, frames, crop=None, depth=3, pad_to=None, copy=True):
         """Generator over an iterable of uint8 BGR frames of one size: yields exactly what
         ``transfer(frame, crop)`` returns for each, in order, but pipelined -- the pinned-memory
         upload of frame i+1 (copy-in stream) and the download of frame i-1 (copy-out stream) overlap the
         kernels of frame i (current stream).  ``depth`` frames are in flight.
+
+        ``copy=False`` yields a view of the pinned download buffer instead of a fresh array: valid until the generator is
+        advanced again (enough for a consumer that writes the frame out before asking for the next one; saves a 25 MB host
+        copy per 1080p frame, which is what limits 8 processes sharing one host).
 
         ``pad_to=(PH, PW)``: the frames are RAW; ReshapeTool.process (generate_real_video.py:66-83, reflect border of 64
         pixels up to PH x PW) runs on the device, and ``crop`` defaults to the raw frame's window (:167)."""
@@ -91,7 +95,8 @@ class Stylization:
 
         def finish(slot):
             slot["ev_out"].synchronize()
-            return slot["host_out"].numpy()[0].copy()
+            out = slot["host_out"].numpy()[0]
+            return out.copy() if copy else out
 
         for i, frame in enumerate(frames):
             frame = np.ascontiguousarray(frame)

@@ -644,6 +644,8 @@ def test_transfer_stream_equals_transfer(L, dev, state_dict):
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
+    for i, a in enumerate(fw.transfer_stream(iter(frames), crop=crop, depth=2, copy=False)):     # zero-copy: valid until the next item
+        assert np.array_equal(a, want[i])
     # pad_to: raw frames, reflect border on the device, cropped back to the raw window (generate_real_video.py:66-83, :167)
     raw = [smooth(40, 56) for _ in range(4)]
     padded = [np.pad(f, ((64, 192 - 64 - 40), (64, 192 - 64 - 56), (0, 0)), mode="symmetric") for f in raw]
