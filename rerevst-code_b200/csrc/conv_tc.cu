@@ -714,8 +714,6 @@ struct Tc2Params {
                             //    along N (N = 4 Cout_pad = [px0 b0 | px0 b1 | px1 b0 | px1 b1]); nph = 2 row phases are the tiles
     int dxm_groups;         // weight tiles per A box: 3 (tap rows dy) or 2 (tap rows a of one row phase)
     int b_parts;            // dxm 2: TMA loads per weight slot and CTA (blocks of Cout_pad blob rows)
-    int tiles_pp;           // dxm 2: tiles per row phase; the row phase is the SLOWEST tile index, so that (b_resident == 2) the
-                            //        2 kchunks weight tiles of a phase are loaded once per phase and worker, not once per tile
     int a_stages, b_slots, b_resident, pair;
     int a_plane_bytes;      // (16 MT + 2) * 1024 (16 MT for 1x1)
     int acc_stride, set_stride, bufs, tmem_cols;
@@ -810,14 +808,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const uint32_t a_plane = (uint32_t)p.a_plane_bytes;
             const bool x3 = p.x3 != 0, resident = p.b_resident != 0, lead = !PAIR || cta_rank == 0;
             const int brow0 = PAIR ? (int)cta_rank * (p.BN / 2) : 0;
-            int prev_ph = -1;
-            uint32_t brel = 0;            // b_resident 2: parity of the "phase drained" completions of s_bempty
             for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
-                const int ph = p.dxm == 2 ? tile / p.tiles_pp : 0;           // dxm 2: the row phase py
-                int t = p.dxm == 2 ? tile % p.tiles_pp : tile;
-                const bool reload = ph != prev_ph;
-                const bool had_phase = prev_ph >= 0;
-                prev_ph = ph;
+                int t = tile;
+                const int ph = t % p.nph; t /= p.nph;                        // dxm 2: the row phase py (fastest: the two phases of a
+                                                                             // spatial tile follow each other, the second A read hits L2)
                 const int bx = ((t % p.tiles_x) * (PAIR ? 2 : 1) + (int)cta_rank) * 30 - 1; t /= p.tiles_x;
                 const int by = (t % p.tiles_y) * 4 + (p.dxm == 2 ? ph - 1 : -1);
                 const int n = t / p.tiles_y;
@@ -834,14 +828,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         if (x3) ptx::tma_load_4d(dst + a_plane, &map_a_lo, full, kc * BK, bx, by, n);
                     }
                     if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
-                    if (p.b_resident == 2 ? !reload : (resident && !first_set)) continue;
+                    if (resident && !first_set) continue;
 #pragma unroll
                     for (int dy = 0; dy < 3; ++dy) {
                         if (dy >= p.dxm_groups) break;
                         int slot;
                         if (resident) {
                             slot = dy * kch + kc;
-                            if (p.b_resident == 2 && had_phase) ptx::mbar_wait(ptx::smem_u32(&s_bempty[slot]), brel);   // old phase drained
                         } else {
                             slot = sb;
                             ptx::mbar_wait(ptx::smem_u32(&s_bempty[sb]), pb ^ 1u);
@@ -878,7 +871,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     }
                 }
                 first_set = false;
-                if (p.b_resident == 2 && reload && had_phase) brel ^= 1u;
             }
         }
     } else if (DXM && warp == 1 && cta_rank == 0) {
@@ -891,14 +883,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const int kch = p.kchunks;
             const uint32_t a_plane = (uint32_t)p.a_plane_bytes;
             const bool x3 = p.x3 != 0, resident = p.b_resident != 0;
-            int prev_ph = -1;
-            uint32_t bfp = 0;             // b_resident 2: parity of this phase's weight loads
             for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
-                const int ph = p.dxm == 2 ? tile / p.tiles_pp : 0;
-                const bool reload = ph != prev_ph;
-                prev_ph = ph;
-                const int nxt = tile + n_workers;
-                const bool last_of_phase = p.b_resident == 2 && (nxt >= p.total_tiles || nxt / p.tiles_pp != ph);
                 ptx::mbar_wait(ptx::smem_u32(&s_tempty[as]), aphase ^ 1u);
                 ptx::tc_fence_after();
                 const uint32_t d0 = tmem_base + (uint32_t)(as * p.set_stride);
@@ -912,8 +897,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         int slot;
                         if (resident) {
                             slot = dy * kch + kc;
-                            if (p.b_resident == 2 ? reload : first_set) {
-                                ptx::mbar_wait(ptx::smem_u32(&s_bfull[slot]), p.b_resident == 2 ? bfp : 0u);
+                            if (first_set) {
+                                ptx::mbar_wait(ptx::smem_u32(&s_bfull[slot]), 0u);
                                 ptx::tc_fence_after();
                             }
                         } else {
@@ -931,9 +916,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             if (PAIR) ptx::mma_commit_pair(ptx::smem_u32(&s_bempty[sb]));
                             else ptx::mma_commit(ptx::smem_u32(&s_bempty[sb]));
                             if (++sb == p.b_slots) { sb = 0; pb ^= 1u; }
-                        } else if (last_of_phase) {          // the producer may overwrite this phase's weights once these MMAs retire
-                            if (PAIR) ptx::mma_commit_pair(ptx::smem_u32(&s_bempty[slot]));
-                            else ptx::mma_commit(ptx::smem_u32(&s_bempty[slot]));
                         }
                     }
                     if (PAIR) {
@@ -946,7 +928,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
                 }
                 first_set = false;
-                if (p.b_resident == 2 && reload) bfp ^= 1u;
                 if (++as == p.bufs) { as = 0; aphase ^= 1u; }
             }
         }
@@ -1087,9 +1068,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         uint32_t aphase = 0;
         for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
             int t = tile;
-            int ph;
-            if (DXM && p.dxm == 2) { ph = t / p.tiles_pp; t %= p.tiles_pp; }       // row phase slowest
-            else { ph = t % p.nph; t /= p.nph; }
+            const int ph = t % p.nph; t /= p.nph;
             const int n0 = (t % p.n_ntiles) * p.BNe; t /= p.n_ntiles;
             const int x0 = ((t % p.tiles_x) * (PAIR ? 2 : 1) + (int)cta_rank) * cols_per_tile; t /= p.tiles_x;
             const int y0 = (t % p.tiles_y) * rows_per_set;
@@ -1414,20 +1393,15 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         d.bufs = 2 * d.set_stride <= 512 ? 2 : 1;
         d.tmem_cols = 32;
         while (d.tmem_cols < d.bufs * d.set_stride) d.tmem_cols *= 2;
-        if (2 * d.kchunks <= MAX_B_SLOTS && 2 * d.kchunks * b_slot + 2 * a_stage <= budget) {
-            // the weight tiles of one row phase stay in shared memory while a worker walks that phase's tiles (reloading them for
-            // every tile makes the layer L2 -> SM bound: 128 KB of weights against 80 KB of activations per tile)
-            d.b_resident = 2; d.b_slots = 2 * d.kchunks;
-            d.a_stages = std::min(MAX_STAGES, (budget - d.b_slots * b_slot) / a_stage);
-        } else {
-            d.b_resident = 0; d.a_stages = 2; d.b_slots = 2;
-            int rem = budget - 2 * a_stage - 2 * b_slot;
-            RRV_REQUIRE(rem >= 0, "rrv_conv2d(tcgen05 v2): merged-phase tile does not fit shared memory");
-            for (;;) {
-                if (d.b_slots < 4 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
-                if (d.a_stages < 3 && rem >= a_stage) { ++d.a_stages; rem -= a_stage; continue; }
-                break;
-            }
+        // weight tiles through the ring (reloaded per tile from L2: keeping one row phase's tiles resident and walking the image
+        // once per phase measured the same and doubles the DRAM reads of the input)
+        d.b_resident = 0; d.a_stages = 2; d.b_slots = 2;
+        int rem = budget - 2 * a_stage - 2 * b_slot;
+        RRV_REQUIRE(rem >= 0, "rrv_conv2d(tcgen05 v2): merged-phase tile does not fit shared memory");
+        for (;;) {
+            if (d.b_slots < 4 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
+            if (d.a_stages < 3 && rem >= a_stage) { ++d.a_stages; rem -= a_stage; continue; }
+            break;
         }
         d.dxm_groups = 2;
         d.b_parts = d.pair ? 2 : 4;
@@ -1568,7 +1542,6 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     const long long total = (long long)d.N * d.tiles_y * d.tiles_x * d.n_ntiles * d.nph;
     RRV_REQUIRE(total < (1LL << 31), "rrv_conv2d: too many tiles");
     d.total_tiles = (int)total;
-    d.tiles_pp = d.dxm == 2 ? d.total_tiles / d.nph : d.total_tiles;
     d.ep = make_epi(p->ep, p->Cout);
     d.ep.lo_fp16 = 0;
 
