@@ -217,18 +217,21 @@ def main():
     fw.prepare_style(style)
 
     # ---- per-clip pre-pass (not part of the timed per-frame loop; reported separately) ----
+    n_samples = max(args.samples, world) if world > 1 else args.samples
+    sample_frames = [synthetic_frame(h, w, 50 + i) for i in range(n_samples)]      # host-side synthesis is not pre-pass time
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     fw.clean()
     if world > 1:
         from rerevst_code_b200.dist import sharded_prepass
-        sharded_prepass(fw, [synthetic_frame(h, w, 50 + i) for i in range(max(args.samples, world))], rank, world)
+        sharded_prepass(fw, sample_frames, rank, world)
     else:
-        for i in range(args.samples):
-            fw.add(synthetic_frame(h, w, 50 + i))
+        for f in sample_frames:
+            fw.add(f)
         fw.compute()
     torch.cuda.synchronize()
     prepass_s = time.perf_counter() - t0
+    del sample_frames
 
     nfr = 4
     host_frames = [reflect_pad(synthetic_frame(h, w, 100 + rank * 16 + i), ph, pw) for i in range(nfr)]
