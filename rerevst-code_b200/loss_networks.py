@@ -63,7 +63,8 @@ def warp_indices(flo):
 class TemporalLoss(torch.nn.Module):
     """The Compound Regularization loss (loss_networks.py:45-111).  ``forward`` is one fused kernel
     (warp + L1 mean) when no gradient is needed, and warp (with backward) + mean otherwise.
-    Fake-flow synthesis (GenerateFakeFlow :71-86, numpy/cv2 on the host) is out of scope; pass a flow."""
+    Fake-flow synthesis (GenerateFakeFlow :71-86) stays on the host in numpy/cv2 like in the reference and draws
+    from ``np.random`` / ``random`` in the reference's order, so equal seeds give the reference's flow."""
 
     def __init__(self, data_sigma=True, data_w=True, noise_level=0.001, motion_level=8, shift_level=10):
         super().__init__()
@@ -74,11 +75,28 @@ class TemporalLoss(torch.nn.Module):
         stddev = stddev + random.random() * stddev
         return ins + torch.empty_like(ins).normal_(mean, stddev)
 
+    def GenerateFakeFlow(self, height, width):
+        """(:71-86) [2, H, W] float32 on the host: low-resolution normal noise (sigma = motion_level px) resized to the frame,
+        a random global shift of up to shift_level px per axis, 100 x 100 box blur."""
+        import cv2
+        import numpy as np
+        if self.motion_level > 0:
+            flow = np.random.normal(0, scale=self.motion_level, size=[height // 100, width // 100, 2])
+            flow = cv2.resize(flow, (width, height))
+            flow[:, :, 0] += random.randint(-self.shift_level, self.shift_level)
+            flow[:, :, 1] += random.randint(-self.shift_level, self.shift_level)
+            flow = cv2.blur(flow, (100, 100))
+        else:
+            flow = np.ones([width, height, 2])       # (sic: the reference builds this case as [W, H, 2], :82)
+            flow[:, :, 0] = random.randint(-self.shift_level, self.shift_level)
+            flow[:, :, 1] = random.randint(-self.shift_level, self.shift_level)
+        return torch.from_numpy(flow.transpose((2, 0, 1))).float()
+
     def GenerateFakeData(self, first_frame, forward_flow=None):
-        """(:88-104) with the flow supplied by the caller ([2,H,W] or [B,2,H,W])."""
+        """(:88-104); the flow is synthesised on the host unless the caller supplies one ([2,H,W] or [B,2,H,W])."""
         if self.data_w:
             if forward_flow is None:
-                raise ValueError("pass forward_flow (host-side fake-flow synthesis is not part of this package)")
+                forward_flow = self.GenerateFakeFlow(first_frame.shape[2], first_frame.shape[3])
             if forward_flow.dim() == 3:
                 forward_flow = forward_flow.unsqueeze(0)
             forward_flow = forward_flow.to(first_frame.device).expand(first_frame.shape[0], 2, *first_frame.shape[2:]).contiguous()

@@ -101,3 +101,24 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("the oracle, ", "").lower() or f == "framework.py", (dirpath, f)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/train"), reason="reference not present")
+def test_fake_flow_equals_live_reference():
+    """TemporalLoss.GenerateFakeFlow (train/loss_networks.py:71-86): host-side numpy/cv2 synthesis drawing from
+    np.random / random in the reference's order -- equal seeds give the reference's flow bit for bit."""
+    import random
+    import sys
+
+    import numpy as np
+    import torch
+    from oracle.make_golden import import_reference
+    from rerevst_code_b200.loss_networks import TemporalLoss
+    ln = import_reference("loss_networks", "train")
+    for (h, w) in ((256, 320), (512, 512)):
+        np.random.seed(0); random.seed(0)
+        ref = ln.TemporalLoss().GenerateFakeFlow(h, w)
+        np.random.seed(0); random.seed(0)
+        got = TemporalLoss().GenerateFakeFlow(h, w)
+        assert got.dtype == torch.float32 and tuple(got.shape) == (2, h, w)
+        assert torch.equal(got, ref)
