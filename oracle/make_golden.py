@@ -153,6 +153,34 @@ def run_train(sd):
     return res
 
 
+def multi_inputs():
+    g = torch.Generator().manual_seed(777)
+    styles = [torch.randn(1, 3, 64, 72, generator=g), torch.randn(1, 3, 56, 64, generator=g)]
+    patches = [torch.randn(1, 3, 48, 64, generator=g) for _ in range(2)]
+    frame = torch.randn(1, 3, 64, 80, generator=g)
+    return styles, patches, frame
+
+
+def run_multi(sd):
+    """"Multi-style Interpolation/style_network.py": two styles, statistics from two patches, three weightings."""
+    m = import_reference("style_network", "Multi-style Interpolation")
+    net = m.TransformerNet(style_num=2).eval()
+    net.load_state_dict(sd, strict=True)
+    styles, patches, frame = multi_inputs()
+    res = {}
+    with torch.no_grad():
+        for i, s in enumerate(styles):
+            net.generate_style_features(s, i)
+        net.clean()
+        for pch in patches:
+            net.add_patch(net.generate_content_features(pch))
+        net.compute_norm()
+        fc = net.generate_content_features(frame)
+        for name, w in (("w10", [1.0, 0.0]), ("w37", [0.3, 0.7]), ("w55", [0.5, 0.5])):
+            res["out/" + name] = net(fc, w).numpy()
+    return res
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     sd = synthetic_state_dict(cases.WEIGHT_SEED)
@@ -165,6 +193,7 @@ def main():
     for name in cases.FRAME_CASES:
         np.savez_compressed(os.path.join(OUT, f"frame_{name}.npz"), **run_frame(name, sd))
     np.savez_compressed(os.path.join(OUT, "train_model.npz"), **run_train(sd))
+    np.savez_compressed(os.path.join(OUT, "multi_style.npz"), **run_multi(sd))
     res, meta = run_warp()
     np.savez_compressed(os.path.join(OUT, "warp.npz"), **res)
     with open(os.path.join(OUT, "warp_digests.json"), "w") as f:

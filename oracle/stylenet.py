@@ -347,6 +347,56 @@ class GlobalOracle:
 
 
 # --------------------------------------------------------------------------------------
+# Multi-style interpolation  ("Multi-style Interpolation/style_network.py")
+
+def blend_states(states, styles, weights):
+    """What the multi-style modules do inside forward (InstanceNorm.forward :35-53, FilterPredictor.forward :135-139,
+    Decoder.AdaIN :348-360): every cached table is the style_weight-ed sum of the per-style tables."""
+    cs = ClipState()
+    for k in states[0].stats:
+        cs.stats[k] = SavedStat(*[sum(w * getattr(st.stats[k], f) for st, w in zip(states, weights)) for f in SavedStat._fields])
+    for k in states[0].filters:
+        cs.filters[k] = tuple(sum(w * st.filters[k][j] for st, w in zip(states, weights)) for j in range(2))
+    blend = lambda lvl: MeanStd(sum(w * getattr(fs, lvl).mean for fs, w in zip(styles, weights)),
+                                sum(w * getattr(fs, lvl).std for fs, w in zip(styles, weights)))
+    fs = StyleFeatures(None, blend("relu1_1"), blend("relu2_1"), blend("relu3_1"), blend("relu4_1"))
+    return cs, fs
+
+
+class MultiStyleOracle:
+    """Call sequence of the multi-style ``TransformerNet`` (:464-497): generate_style_features(style, id),
+    generate_content_features, add_patch, compute_norm, forward(F_content, style_weight)."""
+
+    def __init__(self, state_dict, style_num):
+        self.sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
+        self.F_style = [None] * style_num
+        self.F_patches = []
+        self.states = None
+
+    @torch.no_grad()
+    def generate_style_features(self, style, style_id):
+        self.F_style[style_id] = encoder_style(style, self.sd)
+
+    @torch.no_grad()
+    def generate_content_features(self, content):
+        return encoder(rgb2gray(content), self.sd)
+
+    def add_patch(self, f_patch):
+        self.F_patches.append(f_patch)
+
+    @torch.no_grad()
+    def compute_norm(self):
+        x = torch.cat(self.F_patches, dim=0)
+        self.states = [decoder_compute(self.sd, x, fs) for fs in self.F_style]       # Decoder.compute_norm :415-430, per style
+        self.F_patches = []
+
+    @torch.no_grad()
+    def forward(self, f_content, style_weight=(1.0,)):
+        cs, fs = blend_states(self.states, self.F_style, style_weight)
+        return decoder_forward(self.sd, f_content, fs, cs)
+
+
+# --------------------------------------------------------------------------------------
 # Frame mode  (style_network_frame.py:294-394)
 
 @torch.no_grad()

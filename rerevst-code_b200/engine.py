@@ -370,10 +370,11 @@ class StyleEngine:
         return out
 
     @torch.no_grad()
-    def compute(self):
+    def compute(self, keep_samples=False):
         """Decoder.compute (:425-439): 11 global statistic tables + 6 dynamic filters, stage by stage
         over all sampled frames.  Quirk Q1 is reproduced: only sample 0 goes through the dynamic
-        filters and its residual is broadcast to every sample."""
+        filters and its residual is broadcast to every sample.  keep_samples: the multi-style model runs
+        this once per style on the same sampled frames."""
         if self.style is None:
             raise RuntimeError("compute() before generate_style_features()")
         if not self.samples:
@@ -417,8 +418,9 @@ class StyleEngine:
             st[block + ".norm2"] = self._saved_stat(r2)
             r = self._pointwise(r2, make_epilogue(norm1=st[block + ".norm2"], res=s, res_shift=1), to_f32=True)
             del r2
-        self.samples = []
-        self.q1_sample = None
+        if not keep_samples:
+            self.samples = []
+            self.q1_sample = None
         self._plans = {}
 
     # ------------------------------------------------------------------ per-frame forward
@@ -438,8 +440,29 @@ class StyleEngine:
             N, _, H, W = frame.shape
         else:
             N, H, W, _ = frame.shape
+        h = self._vgg("Encoder", frame.contiguous(), kind, True, N, H, W, "content", norm0=self.stats["norm0"])
+        return self._decode(h, out)
+
+    @torch.no_grad()
+    def encode(self, frame, kind=0):
+        """Encoder(RGB2Gray(frame)) (:280-281, :487-497) -> relu4_1 as the fp32 NCHW view of an NHWC tensor
+        (generate_content_features of the multi-style model)."""
+        if kind == 0:
+            N, _, H, W = frame.shape
+        else:
+            N, H, W, _ = frame.shape
+        return self._vgg("Encoder", frame.contiguous(), kind, True, N, H, W, "raw").permute(0, 3, 1, 2)
+
+    @torch.no_grad()
+    def decode_features(self, f_content, out=None):
+        """Decoder.forward (:441-451) on encoder features [N,512,h,w] (fp32, ideally the view returned by encode())."""
+        self._require_ready()
+        x = f_content.permute(0, 2, 3, 1).contiguous()
+        return self._decode(self._pointwise(x, make_epilogue(norm1=self.stats["norm0"])), out)
+
+    def _decode(self, h, out=None):
+        """norm[0](relu4_1) planes -> Filter1..3 -> AdaIN -> slice4..2 -> slice1 (Decoder.forward :441-451)."""
         st, tabs = self.stats, self.style["tabs"]
-        h = self._vgg("Encoder", frame.contiguous(), kind, True, N, H, W, "content", norm0=st["norm0"])
         for i, f in enumerate(FILTERS):
             down, up = self.fw[f]
             t = self._conv(down, h, make_epilogue(bias=down.bias, act=2))

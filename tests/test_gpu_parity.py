@@ -417,6 +417,27 @@ def test_full_size_raw_1080p_against_oracle(L, dev, state_dict):
     assert rel_linf(got.numpy(), ref.numpy()) < TOL
 
 
+def test_multi_style_interpolation_matches_reference_golden(L, dev, state_dict):
+    """multi_style.TransformerNet against the unmodified "Multi-style Interpolation/style_network.py" (tests/golden/multi_style.npz)."""
+    from oracle.make_golden import multi_inputs
+    from rerevst_code_b200.multi_style import TransformerNet
+    gold = np.load(os.path.join(GOLDEN, "multi_style.npz"))
+    styles, patches, frame = multi_inputs()
+    net = TransformerNet(style_num=2).to(dev)
+    net.load_state_dict(state_dict)
+    for i, s in enumerate(styles):
+        net.generate_style_features(s.to(dev), i)
+    net.clean()
+    for pch in patches:
+        net.add_patch(net.generate_content_features(pch.to(dev)))
+    net.compute_norm()
+    fc = net.generate_content_features(frame.to(dev))
+    for name, w in (("w10", [1.0, 0.0]), ("w37", [0.3, 0.7]), ("w55", [0.5, 0.5])):
+        assert rel_linf(net(fc, w).cpu().numpy(), gold["out/" + name]) < TOL, name
+    with pytest.raises(ValueError):
+        net(fc, [1.0])
+
+
 def test_forward_with_oracle_statistics(L, dev, state_dict):
     """Per-frame forward alone: clip state imported from the oracle, so only forward error counts."""
     from oracle import cases, stylenet

@@ -78,6 +78,22 @@ def test_train_model_matches_golden(state_dict):
     assert abs(float(cl) - float(gold["content_loss"])) < 1e-5 * abs(float(gold["content_loss"]))
 
 
+def test_multi_style_matches_golden(state_dict):
+    """"Multi-style Interpolation/style_network.py" (SURVEY 8f N3): per-style statistics, blended by style_weight in forward."""
+    from oracle.make_golden import multi_inputs
+    gold = np.load(os.path.join(GOLDEN, "multi_style.npz"))
+    styles, patches, frame = multi_inputs()
+    o = stylenet.MultiStyleOracle(state_dict, 2)
+    for i, s in enumerate(styles):
+        o.generate_style_features(s, i)
+    for pch in patches:
+        o.add_patch(o.generate_content_features(pch))
+    o.compute_norm()
+    fc = o.generate_content_features(frame)
+    for name, w in (("w10", [1.0, 0.0]), ("w37", [0.3, 0.7]), ("w55", [0.5, 0.5])):
+        assert rel_linf(o.forward(fc, w).numpy(), gold["out/" + name]) < ORACLE_TOL
+
+
 def test_q1_only_first_sample_is_filtered(state_dict):
     """Quirk Q1: in the pre-pass only sample 0 goes through the dynamic filters and
     its residual is broadcast to every sample."""
