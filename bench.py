@@ -297,7 +297,8 @@ def main():
     eng.profile = []
     eng.forward(dev_frames[0], kind=1, out=out)
     torch.cuda.synchronize()
-    layers = [(lbl, a.elapsed_time(b), fl) for lbl, a, b, fl in eng.profile]
+    layers = [(lbl, a.elapsed_time(b), fl) for lbl, a, b, fl, _ in eng.profile]
+    executed_flops = sum(ex for *_, ex in eng.profile)
     eng.profile = None
     conv_ms = sum(t for _, t, _ in layers)
     conv_flops = sum(f for _, _, f in layers)
@@ -357,6 +358,12 @@ def main():
                             "once: the 3 MMAs of the bf16x3 split are not credited) / summed CUDA-event durations of their launches; "
                             "traffic = DRAM bytes per launch, mean over the frame's conv launches, from profiles/r1_traffic.json",
                      "launches_per_frame": len(layers), "kernel_ms_per_frame": conv_ms,
+                     "executed": {"tflops": executed_flops * (args.steps / (ms_dev * 1e-3)) / 1e12,
+                                  "frac": executed_flops * (args.steps / (ms_dev * 1e-3)) / 1e12 / pk["tflops"],
+                                  "flops_per_frame": executed_flops,
+                                  "note": "tensor work actually issued per frame (x3: three bf16 MMAs per k-slice; nearest-x2 layers: 4 of 9 "
+                                          "taps; padded channels included) x frames/s of the whole frame, against the same peak -- what the "
+                                          "tensor pipes do, as opposed to what the algorithm needs (achieved / frac above)"},
                      "whole_frame": {"achieved": frame_tflops, "frac": frame_tflops / pk["tflops"], "flops_per_frame": fl}},
         "config3_bf16": None if bf16 is None else {
             "value": world * args.steps / (bf16[0] * 1e-3), "unit": "frames/s", "ms_per_step": bf16[0] / args.steps,

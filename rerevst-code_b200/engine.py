@@ -204,8 +204,13 @@ class StyleEngine:
         if self.profile is not None:
             e1.record()
             hin, win = x.H, x.W
+            # executed tensor work: 4 of 9 taps for the nearest-x2 layers, k-slices of 16 real input channels, Cout padded to 16,
+            # three MMAs per k-slice in x3 mode
+            taps = 4 if cw.ups else cw.ksize * cw.ksize
+            k_exec = -(-(cw.Cin_used or cw.Cin) // 16) * 16
+            executed = 2.0 * k_exec * (-(-cw.Cout // 16) * 16) * taps * N * H * W * (3 if x.lo is not None else 1)
             self.profile.append((f"conv{cw.ksize}x{cw.ksize}{'u' if cw.ups else ''} {cw.Cin}->{cw.Cout} @{H}x{W}", e0, e1,
-                                 2.0 * cw.Cin * cw.Cout * cw.ksize * cw.ksize * N * H * W))
+                                 2.0 * cw.Cin * cw.Cout * cw.ksize * cw.ksize * N * H * W, executed))
         return out
 
     def _pointwise(self, x_f32, ep, N=None, broadcast=False, to_f32=False):
