@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RRV_ABI_VERSION 1
+#define RRV_ABI_VERSION 2
 
 /* ---- library ------------------------------------------------------------------------ */
 int         rrv_abi_version(void);
@@ -60,7 +60,14 @@ typedef struct rrv_epilogue {
                              * kept in fp32 -- the same bytes as two 16-bit planes, one add instead of unpack + two */
 } rrv_epilogue;
 
-enum { RRV_OUT_PLANES = 0, RRV_OUT_F32_NHWC = 1, RRV_OUT_F32_NCHW = 2 };
+/* RRV_OUT_BGR_F32 / RRV_OUT_BGR_U8 (the RGB head, Cout == 3): transform_back_image + tensor2numpy (test/framework.py:39-49)
+ * and the crop of generate_real_video.py:167 run in the convolution's epilogue; the output is the HWC BGR frame
+ * [N][crop_h][crop_w][3] in [0,255], fp32 (what Stylization.transfer returns) or uint8 (rint, what cv2.imwrite makes of it). */
+enum { RRV_OUT_PLANES = 0, RRV_OUT_F32_NHWC = 1, RRV_OUT_F32_NCHW = 2, RRV_OUT_BGR_F32 = 3, RRV_OUT_BGR_U8 = 4 };
+/* Operand terms of the fp32-accurate split (in_lo != NULL).  FULL: hi*Whi + hi*Wlo + lo*Whi (three MMAs per k-slice);
+ * NO_WLO drops hi*Wlo (weights enter at bf16 precision), NO_ALO drops lo*Whi (activations enter at bf16 precision): two MMAs.
+ * oracle/precision_sweep.py measures what each layer tolerates. */
+enum { RRV_TERMS_FULL = 0, RRV_TERMS_NO_WLO = 1, RRV_TERMS_NO_ALO = 2 };
 enum { RRV_IMPL_FFMA = 0, RRV_IMPL_TCGEN05 = 1 };
 
 /* ---- convolution ---------------------------------------------------------------------- */
@@ -89,6 +96,9 @@ typedef struct rrv_conv {
     int32_t pool;           /* 1: nn.MaxPool2d(2, 2) (vgg19.features[4|9|18], floor) fused behind bias + activation; the
                              * planes output is [N][H/2][W/2][Cout].  tcgen05 path, ups == 0, Cout % 32 == 0, no norm /
                              * residual / affine stage. */
+    int32_t terms;          /* RRV_TERMS_* (tcgen05 path with lo planes) */
+    void*   out_img;        /* RRV_OUT_BGR_*: [N][crop_h][crop_w][3] fp32 or uint8 */
+    int32_t crop_y0, crop_x0, crop_h, crop_w;   /* RRV_OUT_BGR_*: window of the H x W result that is kept */
 } rrv_conv;
 
 int rrv_conv2d(const rrv_conv* p, int impl, void* stream);
@@ -147,6 +157,10 @@ int rrv_reflect_pad_u8(const void* src, int N, int H, int W, int top, int left, 
  * (generate_real_video.py:167). */
 int rrv_postprocess_bgr(const float* in, int N, int H, int W, int y0, int x0, int h, int w,
                         float* out, void* stream);
+/* Same, rounded to uint8 (rint of the clamped value: what cv2.imwrite's float32 -> uint8 conversion stores,
+ * generate_real_video.py:170); a quarter of the bytes to download. */
+int rrv_postprocess_bgr_u8(const float* in, int N, int H, int W, int y0, int x0, int h, int w,
+                           uint8_t* out, void* stream);
 
 /* ---- statistics ------------------------------------------------------------------------ */
 /* Per-channel partial statistics of an fp32 NHWC tensor over (N,H,W):

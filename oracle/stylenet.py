@@ -9,8 +9,8 @@ written against a plain 107-key ``state_dict``.  All arithmetic goes through the
 same third-party library the reference uses (PyTorch CPU ops: ``F.conv2d``,
 ``F.max_pool2d``, ``F.interpolate``, ``torch.mean/max/min/rsqrt``), so on
 identical weights and inputs it reproduces the reference bit for bit; this is
-pinned by ``tests/test_oracle_vs_reference.py`` (runs where ``/root/reference``
-exists) and by the committed fixtures under ``tests/golden/`` that
+pinned by ``tests/test_oracle.py::test_oracle_equals_live_reference`` (runs where
+``/root/reference`` exists) and by the committed fixtures under ``tests/golden/`` that
 ``oracle/make_golden.py`` generated from the unmodified reference modules.
 
 Reference files restated here (paths relative to the reference repo):
@@ -308,11 +308,23 @@ class GlobalOracle:
     """Same call sequence as the reference ``TransformerNet`` in global mode
     (style_network_global.py:454-501): generate_style_features, clean, add, compute, forward."""
 
-    def __init__(self, state_dict):
-        self.sd = {k: v.detach().float().cpu() for k, v in state_dict.items()}
+    def __init__(self, state_dict, device="cpu"):
+        """device="cpu" is the oracle.  Any other device runs the SAME functional code through PyTorch's eager kernels there
+        (cuDNN on CUDA): bench.py's ``gpu_baseline`` -- what the reference itself does on a GPU (test/framework.py:61-65)."""
+        self.device = torch.device(device)
+        self.sd = {k: v.detach().float().to(self.device) for k, v in state_dict.items()}
         self.F_style = None
         self.clip = None
         self.F_patches = None
+
+    def to_device_state(self, clip: "ClipState", fs: "StyleFeatures"):
+        """Adopt per-clip tables / style statistics computed elsewhere (moved to this oracle's device)."""
+        mv = lambda t: None if t is None else t.to(self.device)
+        c = ClipState()
+        c.stats = {k: SavedStat(*[mv(t) for t in v]) for k, v in clip.stats.items()}
+        c.filters = {k: tuple(mv(t) for t in v) for k, v in clip.filters.items()}
+        self.clip = c
+        self.F_style = StyleFeatures(mv(fs.map), *[MeanStd(mv(m.mean), mv(m.std)) for m in fs[1:]])
 
     @torch.no_grad()
     def generate_style_features(self, style):

@@ -12,7 +12,9 @@ import torch  # noqa: F401  (loads libcudart.so.12 into the process before our l
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RRV_LIB_PATH") or os.path.join(_HERE, "csrc", "librerevst_b200.so")   # override: kernel experiments
 
-OUT_PLANES, OUT_F32_NHWC, OUT_F32_NCHW = 0, 1, 2
+OUT_PLANES, OUT_F32_NHWC, OUT_F32_NCHW, OUT_BGR_F32, OUT_BGR_U8 = 0, 1, 2, 3, 4
+TERMS_FULL, TERMS_NO_WLO, TERMS_NO_ALO = 0, 1, 2
+ABI_VERSION = 2
 IMPL_FFMA, IMPL_TCGEN05 = 0, 1
 
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
@@ -30,7 +32,8 @@ class Conv(C.Structure):
     _fields_ = [("N", _i32), ("H", _i32), ("W", _i32), ("Cin", _i32), ("Cout", _i32), ("ksize", _i32),
                 ("ups", _i32), ("in_hi", _vp), ("in_lo", _vp), ("w_f32", _vp), ("w_tc", _vp),
                 ("ep", Epilogue), ("out_mode", _i32), ("out_hi", _vp), ("out_lo", _vp), ("out_f32", _vp),
-                ("out_C", _i32), ("Cin_used", _i32), ("pool", _i32)]
+                ("out_C", _i32), ("Cin_used", _i32), ("pool", _i32), ("terms", _i32), ("out_img", _vp),
+                ("crop_y0", _i32), ("crop_x0", _i32), ("crop_h", _i32), ("crop_w", _i32)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/rerevst_b200.h
@@ -56,6 +59,7 @@ SIGNATURES = {
     "rrv_nchw_to_planes": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "rrv_reflect_pad_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rrv_postprocess_bgr": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "rrv_postprocess_bgr_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rrv_channel_stats": (C.c_int, [_vp, _i64, C.c_int, _vp, _vp]),
     "rrv_stats_merge": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "rrv_stats_finalize": (C.c_int, [_vp, C.c_int, C.c_int, C.c_float, _vp, _vp]),
@@ -80,7 +84,7 @@ def lib():
             fn = getattr(handle, name)      # AttributeError if a declared symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.rrv_abi_version() != 1:
+        if handle.rrv_abi_version() != ABI_VERSION:
             raise RuntimeError("librerevst_b200.so: ABI version mismatch")
         _lib = handle
     return _lib

@@ -45,6 +45,7 @@ int pointwise(const float* in, long long in_bs, int N, int H, int W, int C, cons
 int planes_to_nchw(const void* hi, const void* lo, int N, int H, int W, int C, float* out, cudaStream_t st);
 int nchw_to_planes(const float* in, int N, int H, int W, int C, void* hi, void* lo, cudaStream_t st);
 int postprocess_bgr(const float* in, int N, int H, int W, int y0, int x0, int h, int w, float* out, cudaStream_t st);
+int postprocess_bgr_u8(const float* in, int N, int H, int W, int y0, int x0, int h, int w, uint8_t* out, cudaStream_t st);
 int pack_weights_f32(const float* w, int Cin, int Cout, int ksize, int Cin_pad, int Cout_pad, float* out, cudaStream_t st);
 int channel_stats(const float* x, long long npix, int C, double* part, cudaStream_t st);
 int stats_merge(const double* parts, int nparts, int C, double* merged, cudaStream_t st);
@@ -112,6 +113,9 @@ int rrv_nchw_to_planes(const float* in, int N, int H, int W, int C, void* hi, vo
 }
 int rrv_postprocess_bgr(const float* in, int N, int H, int W, int y0, int x0, int h, int w, float* out, void* stream) {
     return postprocess_bgr(in, N, H, W, y0, x0, h, w, out, ST(stream));
+}
+int rrv_postprocess_bgr_u8(const float* in, int N, int H, int W, int y0, int x0, int h, int w, uint8_t* out, void* stream) {
+    return postprocess_bgr_u8(in, N, H, W, y0, x0, h, w, out, ST(stream));
 }
 int rrv_channel_stats(const float* x, int64_t npix, int C, double* part, void* stream) {
     return channel_stats(x, npix, C, part, ST(stream));

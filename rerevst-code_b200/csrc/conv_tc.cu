@@ -78,6 +78,8 @@ struct OutDesc {
     uint16_t* out_hi;
     uint16_t* out_lo;
     float* out_f32;
+    void* out_img;                       // RRV_OUT_BGR_*: the post-processed, cropped HWC BGR frame
+    int crop_y0, crop_x0, crop_h, crop_w;
 };
 
 struct TcParams {
@@ -227,11 +229,29 @@ __device__ __forceinline__ void store_group(const OutDesc& p, const float* v, co
             for (int k = 0; k < 8; ++k)
                 if (k < nvalid) o[k] = v[k];
         }
-    } else {
+    } else if (p.out_mode == RRV_OUT_F32_NCHW) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
             if (k < nvalid && c0 + k < p.out_C)
                 p.out_f32[(((long long)px.n * p.out_C + c0 + k) * p.H + px.oy) * p.W + px.ox] = v[k];
+    } else {
+        // the RGB head with transform_back_image + tensor2numpy (test/framework.py:39-49) and the crop of
+        // generate_real_video.py:167 fused in: img * std + mean (two roundings like the reference's tensor ops), clamp(0, 1),
+        // * 255, RGB -> BGR, HWC
+        if (c0 != 0) return;
+        const int yy = px.oy - p.crop_y0, xx = px.ox - p.crop_x0;
+        if (yy < 0 || yy >= p.crop_h || xx < 0 || xx >= p.crop_w) return;
+        const float r = __fmul_rn(fminf(fmaxf(__fadd_rn(__fmul_rn(v[0], 0.229f), 0.485f), 0.0f), 1.0f), 255.0f);
+        const float g = __fmul_rn(fminf(fmaxf(__fadd_rn(__fmul_rn(v[1], 0.224f), 0.456f), 0.0f), 1.0f), 255.0f);
+        const float b = __fmul_rn(fminf(fmaxf(__fadd_rn(__fmul_rn(v[2], 0.225f), 0.406f), 0.0f), 1.0f), 255.0f);
+        const long long off = (((long long)px.n * p.crop_h + yy) * p.crop_w + xx) * 3;
+        if (p.out_mode == RRV_OUT_BGR_F32) {
+            float* o = reinterpret_cast<float*>(p.out_img) + off;
+            o[0] = b; o[1] = g; o[2] = r;
+        } else {
+            uint8_t* o = reinterpret_cast<uint8_t*>(p.out_img) + off;       // cv2.imwrite: saturate_cast<uchar>(cvRound(v))
+            o[0] = (uint8_t)__float2int_rn(b); o[1] = (uint8_t)__float2int_rn(g); o[2] = (uint8_t)__float2int_rn(r);
+        }
     }
 }
 
@@ -625,7 +645,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 const uint32_t sb = smem_base + (uint32_t)stage * stage_bytes;
                 const uint32_t empty_bar = ptx::smem_u32(&s_empty[stage]), tfull_bar = ptx::smem_u32(&s_tfull[as]);
                 if (ptx::elect_one()) {
-                    ptx::mma_kblock(d_tmem, sb, sb + off_a_lo, sb + off_b_hi, sb + off_b_lo, idesc, p.x3 != 0, ks == 0);
+                    ptx::mma_kblock(d_tmem, sb, sb + off_a_lo, sb + off_b_hi, sb + off_b_lo, idesc, p.x3 ? 3u : 0u, ks == 0);
                     ptx::mma_commit(empty_bar);                               // frees the smem slot when the MMAs retire
                     if (ks == ksteps - 1) ptx::mma_commit(tfull_bar);
                 }
@@ -706,7 +726,8 @@ struct Tc2Params {
     int ngrp[4][3];
     Grp grp[4][3][3];
     int tiles_x, tiles_y, n_ntiles, total_tiles;
-    int BN, x3;             // BN = N of the MMA (3 Cout_pad when the dy taps are merged)
+    int BN, x3;             // BN = N of the MMA (3 Cout_pad when the dy taps are merged); x3: lo planes present
+    int terms;              // MMAs per k-slice beyond hi*Whi: bit 0 = hi*Wlo, bit 1 = lo*Whi (3 = the full fp32-accurate split)
     int BNe;                // output channels per tile (= BN, or Cout_pad when merged)
     int b_tile_rows;        // blob rows per weight tile index (Cout_pad, or 3 Cout_pad when merged)
     int dxm;                // 1: dx taps merged along N: M tile = 4 rows x 32 columns (30 outputs), one TMEM lane quadrant per row
@@ -882,7 +903,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             bool first_set = true;
             const int kch = p.kchunks;
             const uint32_t a_plane = (uint32_t)p.a_plane_bytes;
-            const bool x3 = p.x3 != 0, resident = p.b_resident != 0;
+            const uint32_t x3 = (uint32_t)p.terms;
+            const bool resident = p.b_resident != 0;
             for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
                 ptx::mbar_wait(ptx::smem_u32(&s_tempty[as]), aphase ^ 1u);
                 ptx::tc_fence_after();
@@ -1022,16 +1044,16 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         const uint32_t nk = kc == p.kchunks - 1 ? (uint32_t)p.nk_last : 4u;
                         if (ptx::elect_one()) {
                             if (PAIR) {
-                                ptx::mma_kblock_pair(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, p.x3 != 0, overwrite, nk);
+                                ptx::mma_kblock_pair(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, (uint32_t)p.terms, overwrite, nk);
                                 if (p.MT == 2)
                                     ptx::mma_kblock_pair(d0 + (uint32_t)p.acc_stride, a0 + 16384u, a0 + 16384u + (uint32_t)p.a_plane_bytes, bs,
-                                                         bs + b_plane_bytes, idesc, p.x3 != 0, overwrite, nk);
+                                                         bs + b_plane_bytes, idesc, (uint32_t)p.terms, overwrite, nk);
                                 if (!p.b_resident) ptx::mma_commit_pair(bempty_bar);
                             } else {
-                                ptx::mma_kblock(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, p.x3 != 0, overwrite, nk);
+                                ptx::mma_kblock(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, (uint32_t)p.terms, overwrite, nk);
                                 if (p.MT == 2)
                                     ptx::mma_kblock(d0 + (uint32_t)p.acc_stride, a0 + 16384u, a0 + 16384u + (uint32_t)p.a_plane_bytes, bs,
-                                                    bs + b_plane_bytes, idesc, p.x3 != 0, overwrite, nk);
+                                                    bs + b_plane_bytes, idesc, (uint32_t)p.terms, overwrite, nk);
                                 if (!p.b_resident) ptx::mma_commit(bempty_bar);
                             }
                         }
@@ -1264,6 +1286,8 @@ OutDesc make_out(const rrv_conv* p) {
     o.pool = p->pool ? 1 : 0;
     o.H = p->H >> o.pool; o.W = p->W >> o.pool; o.Cout = p->Cout; o.out_mode = p->out_mode; o.out_C = p->out_C;
     o.out_hi = (uint16_t*)p->out_hi; o.out_lo = (uint16_t*)p->out_lo; o.out_f32 = p->out_f32;
+    o.out_img = p->out_img;
+    o.crop_y0 = p->crop_y0; o.crop_x0 = p->crop_x0; o.crop_h = p->crop_h; o.crop_w = p->crop_w;
     return o;
 }
 
@@ -1361,6 +1385,7 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         d.nk_last = (p->Cin_used - (d.kchunks - 1) * BK + 15) / 16;
     }
     d.x3 = p->in_lo != nullptr;
+    d.terms = !d.x3 ? 0 : (p->terms == RRV_TERMS_NO_WLO ? 2 : (p->terms == RRV_TERMS_NO_ALO ? 1 : 3));
     d.nph = ups ? 4 : 1;
     const int halo = (p->ksize == 3) ? 1 : 0;
     const int planes = d.x3 ? 2 : 1;
@@ -1417,8 +1442,11 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         d.MT = 1;
         d.BN = 3 * d.Cout_pad; d.BNe = d.Cout_pad; d.b_tile_rows = 3 * d.Cout_pad;
         d.n_ntiles = 1;
-        // (the RGB head, N = 48, stays single-CTA unless pair_min_bn is lowered: each CTA of a pair holds BN / 2 weight rows)
-        d.pair = (g_tune.pair && num_sms() % 2 == 0 && d.BN >= g_tune.pair_min_bn && (d.BN / 2) % 8 == 0) ? 1 : 0;
+        // (each CTA of a pair holds BN / 2 weight rows: whole 8-row swizzle atoms.  The RGB head, N = 48, is a pair too -- its MMAs
+        //  cost their A fetch, 64 cycles, whatever N is, and a pair covers twice the pixels per MMA; RRV_HEAD_PAIR=0 is the A/B switch)
+        static const bool head_pair = !(getenv("RRV_HEAD_PAIR") && atoi(getenv("RRV_HEAD_PAIR")) == 0);
+        const int min_bn = head_pair ? std::min(g_tune.pair_min_bn, 48) : g_tune.pair_min_bn;
+        d.pair = (g_tune.pair && num_sms() % 2 == 0 && d.BN >= min_bn && (d.BN / 2) % 8 == 0) ? 1 : 0;
         d.a_plane_bytes = 6 * 4096;
         a_stage = planes * d.a_plane_bytes;
         b_slot = planes * d.BN * 128 / (d.pair ? 2 : 1);
@@ -1657,10 +1685,19 @@ int conv2d_tc(const rrv_conv* p, cudaStream_t st) {
         RRV_REQUIRE(p->out_hi != nullptr, "rrv_conv2d: out_hi is NULL");
         RRV_REQUIRE(p->Cout % 8 == 0, "rrv_conv2d: planes output needs Cout %% 8 == 0");
         RRV_REQUIRE((p->in_lo == nullptr) == (p->out_lo == nullptr), "rrv_conv2d: planes in/out must both be x3 or both bf16");
+    } else if (p->out_mode == RRV_OUT_BGR_F32 || p->out_mode == RRV_OUT_BGR_U8) {
+        RRV_REQUIRE(p->out_img != nullptr, "rrv_conv2d: out_img is NULL");
+        RRV_REQUIRE(p->Cout == 3 && !p->pool, "rrv_conv2d: the BGR frame output belongs to the 3-channel RGB head");
+        RRV_REQUIRE(p->crop_h > 0 && p->crop_w > 0 && p->crop_y0 >= 0 && p->crop_x0 >= 0 && p->crop_y0 + p->crop_h <= p->H &&
+                        p->crop_x0 + p->crop_w <= p->W,
+                    "rrv_conv2d: crop window (%d,%d,%d,%d) outside the %dx%d result", p->crop_y0, p->crop_x0, p->crop_h, p->crop_w, p->H, p->W);
+        RRV_REQUIRE(g_tune.version == 2, "rrv_conv2d: the BGR frame output needs the v2 main loop");
     } else {
+        RRV_REQUIRE(p->out_mode == RRV_OUT_F32_NHWC || p->out_mode == RRV_OUT_F32_NCHW, "rrv_conv2d: unknown out_mode %d", p->out_mode);
         RRV_REQUIRE(p->out_f32 != nullptr, "rrv_conv2d: out_f32 is NULL");
         RRV_REQUIRE(p->out_mode != RRV_OUT_F32_NCHW || p->out_C > 0, "rrv_conv2d: out_C must be set for NCHW output");
     }
+    RRV_REQUIRE(p->terms >= RRV_TERMS_FULL && p->terms <= RRV_TERMS_NO_ALO, "rrv_conv2d: bad terms %d", p->terms);
 
     if (p->pool) {
         RRV_REQUIRE(!ups && p->out_mode == RRV_OUT_PLANES && p->Cout % 32 == 0 && g_tune.version == 2,

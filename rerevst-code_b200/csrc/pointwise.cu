@@ -149,8 +149,9 @@ int nchw_to_planes(const float* in, int N, int H, int W, int C, void* hi, void* 
 }
 
 // ---- transform_back_image + tensor2numpy (test/framework.py:39-49) + crop (generate_real_video.py:167) ----
+template <typename T>
 __global__ void __launch_bounds__(256) postprocess_kernel(const float* __restrict__ in, int N, int H, int W, int y0, int x0,
-                                                          int h, int w, float* __restrict__ out) {
+                                                          int h, int w, T* __restrict__ out) {
     const float mean[3] = {0.485f, 0.456f, 0.406f};
     const float sd[3] = {0.229f, 0.224f, 0.225f};
     const long long total = (long long)N * h * w;
@@ -167,8 +168,12 @@ __global__ void __launch_bounds__(256) postprocess_kernel(const float* __restric
             v = fminf(fmaxf(v, 0.0f), 1.0f);                    // clamp(0, 1)
             bgr[2 - c] = __fmul_rn(v, 255.0f);                  // * 255, RGB -> BGR
         }
-        float* o = out + i * 3;
-        o[0] = bgr[0]; o[1] = bgr[1]; o[2] = bgr[2];
+        T* o = out + i * 3;
+        if (sizeof(T) == 1) {            // cv2.imwrite's float32 -> uint8: saturate_cast<uchar>(cvRound(v)), ties to even
+            o[0] = (T)__float2int_rn(bgr[0]); o[1] = (T)__float2int_rn(bgr[1]); o[2] = (T)__float2int_rn(bgr[2]);
+        } else {
+            o[0] = (T)bgr[0]; o[1] = (T)bgr[1]; o[2] = (T)bgr[2];
+        }
     }
 }
 
@@ -211,8 +216,18 @@ int postprocess_bgr(const float* in, int N, int H, int W, int y0, int x0, int h,
     const long long total = (long long)N * h * w;
     if (total == 0) return 0;
     const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
-    postprocess_kernel<<<grid, 256, 0, st>>>(in, N, H, W, y0, x0, h, w, out);
+    postprocess_kernel<float><<<grid, 256, 0, st>>>(in, N, H, W, y0, x0, h, w, out);
     return check_launch("postprocess_kernel");
+}
+
+int postprocess_bgr_u8(const float* in, int N, int H, int W, int y0, int x0, int h, int w, uint8_t* out, cudaStream_t st) {
+    RRV_REQUIRE(in && out, "rrv_postprocess_bgr_u8: NULL tensor");
+    RRV_REQUIRE(y0 >= 0 && x0 >= 0 && y0 + h <= H && x0 + w <= W, "rrv_postprocess_bgr_u8: crop outside the image");
+    const long long total = (long long)N * h * w;
+    if (total == 0) return 0;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 16);
+    postprocess_kernel<uint8_t><<<grid, 256, 0, st>>>(in, N, H, W, y0, x0, h, w, out);
+    return check_launch("postprocess_kernel<u8>");
 }
 
 // ---- fp32 weight repack: OIHW -> [k*k][Cin_pad][Cout_pad], zero padded ----

@@ -137,16 +137,14 @@ __device__ __forceinline__ void mma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint
 // Addresses are shared-memory byte addresses of the hi / lo operand planes; called by ONE thread.
 // nk < 4: only the first nk k-slices carry non-zero weights (input channels padded up to the 64-channel chunk).
 __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                           uint32_t idesc, bool x3, bool overwrite, uint32_t nk = 4) {
+                                           uint32_t idesc, uint32_t terms, bool overwrite, uint32_t nk = 4) {
     const uint32_t ah = desc_lo_sw128(a_hi), al = desc_lo_sw128(a_lo), bh = desc_lo_sw128(b_hi), bl = desc_lo_sw128(b_lo);
 #pragma unroll
     for (uint32_t k = 0; k < 4; ++k) {           // 16 bf16 = 32 bytes = 2 descriptor units per k-slice
         if (k >= nk) break;
         mma_bf16_lo(d_tmem, ah + 2 * k, bh + 2 * k, idesc, (overwrite && k == 0) ? 0u : 1u);
-        if (x3) {
-            mma_bf16_lo(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1u);
-            mma_bf16_lo(d_tmem, al + 2 * k, bh + 2 * k, idesc, 1u);
-        }
+        if (terms & 1u) mma_bf16_lo(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1u);      // hi * Wlo
+        if (terms & 2u) mma_bf16_lo(d_tmem, al + 2 * k, bh + 2 * k, idesc, 1u);      // lo * Whi
     }
 }
 
@@ -216,16 +214,14 @@ __device__ __forceinline__ void mma_bf16_lo_pair(uint32_t d_tmem, uint32_t a_lo,
         : "memory");
 }
 __device__ __forceinline__ void mma_kblock_pair(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                                uint32_t idesc, bool x3, bool overwrite, uint32_t nk = 4) {
+                                                uint32_t idesc, uint32_t terms, bool overwrite, uint32_t nk = 4) {
     const uint32_t ah = desc_lo_sw128(a_hi), al = desc_lo_sw128(a_lo), bh = desc_lo_sw128(b_hi), bl = desc_lo_sw128(b_lo);
 #pragma unroll
     for (uint32_t k = 0; k < 4; ++k) {
         if (k >= nk) break;
         mma_bf16_lo_pair(d_tmem, ah + 2 * k, bh + 2 * k, idesc, (overwrite && k == 0) ? 0u : 1u);
-        if (x3) {
-            mma_bf16_lo_pair(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1u);
-            mma_bf16_lo_pair(d_tmem, al + 2 * k, bh + 2 * k, idesc, 1u);
-        }
+        if (terms & 1u) mma_bf16_lo_pair(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1u);
+        if (terms & 2u) mma_bf16_lo_pair(d_tmem, al + 2 * k, bh + 2 * k, idesc, 1u);
     }
 }
 // Arrives on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs have completed.

@@ -11,7 +11,7 @@ Reference being replaced: ``test/style_network_global.py`` (Encoder :271-281, En
 from __future__ import annotations
 
 import ctypes as C
-from collections import namedtuple
+from collections import OrderedDict, namedtuple
 
 import torch
 
@@ -102,6 +102,8 @@ def make_epilogue(bias=None, act=0, norm1=None, res=None, res_shift=0, res_broad
 class StyleEngine:
     """Everything ``TransformerNet`` needs on one GPU."""
 
+    MAX_PLANS = 3          # captured CUDA graphs kept (LRU by input shape)
+
     def __init__(self, device, precision="x3", impl="auto"):
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -119,7 +121,7 @@ class StyleEngine:
         self.samples = []
         self.q1_sample = None        # Encoder output of the clip's first sampled frame when it lives on another rank (dist.py)
         self.stats_allgather = None  # set by dist.ShardedPrepass: part[5,C] -> parts[G,5,C]
-        self._plans = {}
+        self._plans = OrderedDict()
         self.profile = None          # list -> (label, start_event, end_event, flops) per conv launch (bench.py)
         self.graph_launches = 0      # kernels launched through CUDA-graph replays (not seen by rrv_launch_count)
 
@@ -168,13 +170,13 @@ class StyleEngine:
                         fc=[(g(p + f"{q}.FC.weight").contiguous(), g(p + f"{q}.FC.bias").contiguous()) for q in ("F1", "F2")])
         self.w = w
         self.fw = {}
-        self._plans = {}
+        self._plans = OrderedDict()
         if self.filters:                       # re-fold cached filters against the new weights
             for f, (a, b) in self.filters.items():
                 self._fold_filter(f, a, b)
 
     # ------------------------------------------------------------------ thin wrappers over the C ABI
-    def _conv(self, cw, x, ep, out_mode=L.OUT_PLANES, out=None, N=None, out_C=0, pool=False):
+    def _conv(self, cw, x, ep, out_mode=L.OUT_PLANES, out=None, N=None, out_C=0, pool=False, crop=None, terms=0):
         N = x.N if N is None else N
         H, W = (x.H * 2, x.W * 2) if cw.ups else (x.H, x.W)
         if pool and (self._impl_for(cw) != L.IMPL_TCGEN05 or cw.Cout % 32 != 0 or H < 2 or W < 2):
@@ -188,14 +190,27 @@ class StyleEngine:
         d.out_mode = out_mode
         d.pool = int(pool)
         d.Cin_used = cw.Cin_used
-        if out_mode == L.OUT_PLANES:
+        d.terms = terms
+        if out_mode in (L.OUT_BGR_F32, L.OUT_BGR_U8):      # the RGB head writes the post-processed, cropped HWC BGR frame
+            y0, x0, h, w = crop if crop is not None else (0, 0, H, W)
+            dt = torch.float32 if out_mode == L.OUT_BGR_F32 else torch.uint8
+            out = out if out is not None else torch.empty((N, h, w, 3), dtype=dt, device=self.device)
+            if tuple(out.shape) != (N, h, w, 3) or out.dtype != dt or not out.is_contiguous():
+                raise ValueError(f"frame output is {tuple(out.shape)} {out.dtype}, expected contiguous {dt} {(N, h, w, 3)}")
+            d.out_img = out.data_ptr()
+            d.crop_y0, d.crop_x0, d.crop_h, d.crop_w = y0, x0, h, w
+        elif out_mode == L.OUT_PLANES:
             out = out or Planes(N, H >> int(pool), W >> int(pool), cw.Cout, self.x3, self.device)
+            if (out.N, out.H, out.W, out.C) != (N, H >> int(pool), W >> int(pool), cw.Cout):
+                raise ValueError(f"conv output planes are {(out.N, out.H, out.W, out.C)}, expected {(N, H >> int(pool), W >> int(pool), cw.Cout)}")
             d.out_hi, d.out_lo = L.ptr(out.hi), L.ptr(out.lo)
         elif out_mode == L.OUT_F32_NHWC:
             out = out if out is not None else torch.empty((N, H, W, cw.Cout), dtype=torch.float32, device=self.device)
+            self._check_out(out, (N, H, W, cw.Cout))
             d.out_f32 = out.data_ptr()
         else:
             out = out if out is not None else torch.empty((N, out_C, H, W), dtype=torch.float32, device=self.device)
+            self._check_out(out, (N, out_C, H, W))
             d.out_f32, d.out_C = out.data_ptr(), out_C
         if self.profile is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -212,6 +227,20 @@ class StyleEngine:
             self.profile.append((f"conv{cw.ksize}x{cw.ksize}{'u' if cw.ups else ''} {cw.Cin}->{cw.Cout} @{H}x{W}", e0, e1,
                                  2.0 * cw.Cin * cw.Cout * cw.ksize * cw.ksize * N * H * W, executed))
         return out
+
+    @staticmethod
+    def _check_out(out, shape):
+        """A caller-supplied fp32 output must be exactly the tensor the kernel writes (contiguous, right shape): the kernels
+        compute their own strides from the convolution's size."""
+        if tuple(out.shape) != tuple(shape) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError(f"conv output tensor is {tuple(out.shape)} {out.dtype} (contiguous={out.is_contiguous()}), "
+                             f"expected contiguous float32 {tuple(shape)}")
+
+    @staticmethod
+    def output_size(H, W):
+        """Spatial size of TransformerNet.forward's result for an H x W input: three floor max-pools (vgg19.features[4|9|18])
+        then three nearest x2 upsamples -- (H // 8) * 8, e.g. 436 x 1024 -> 432 x 1024, like the reference."""
+        return (H // 8) * 8, (W // 8) * 8
 
     def _pointwise(self, x_f32, ep, N=None, broadcast=False, to_f32=False):
         n_in, H, W, Cc = x_f32.shape
@@ -313,7 +342,7 @@ class StyleEngine:
         self.style = dict(tabs=tabs, map=smap, nstyle=nstyle)
         ms = {k: mean_std(v[1].view(1, -1, 1, 1), v[0].view(1, -1, 1, 1)) for k, v in tabs.items()}
         self.F_style = vgg_outputs_super(smap.permute(0, 3, 1, 2), ms["relu1_1"], ms["relu2_1"], ms["relu3_1"], ms["relu4_1"])
-        self._plans = {}
+        self._plans = OrderedDict()
 
     # ------------------------------------------------------------------ pre-pass
     def clean(self):
@@ -322,7 +351,7 @@ class StyleEngine:
         self.stats = {}
         self.filters = {}
         self.fw = {}
-        self._plans = {}
+        self._plans = OrderedDict()
 
     @torch.no_grad()
     def add(self, patch, kind=0):
@@ -426,7 +455,7 @@ class StyleEngine:
         if not keep_samples:
             self.samples = []
             self.q1_sample = None
-        self._plans = {}
+        self._plans = OrderedDict()
 
     # ------------------------------------------------------------------ per-frame forward
     def _require_ready(self):
@@ -437,16 +466,19 @@ class StyleEngine:
                                "(the reference fails here with AttributeError: 'NoneType' has no attribute 'expand')")
 
     @torch.no_grad()
-    def forward(self, frame, kind=0, out=None):
+    def forward(self, frame, kind=0, out=None, post=None):
         """TransformerNet.forward (:499-501) for a batch of independent frames.
-        frame: fp32 NCHW normalised (kind 0) or uint8 NHWC BGR (kind 1).  Returns fp32 NCHW."""
+        frame: fp32 NCHW normalised (kind 0) or uint8 NHWC BGR (kind 1).  Returns fp32 NCHW, or with
+        ``post = ("f32" | "u8", (y0, x0, h, w) | None)`` the finished frame of framework.transfer: transform_back_image +
+        tensor2numpy (test/framework.py:39-49) and the crop of generate_real_video.py:167 run in the RGB head's epilogue and the
+        result is [N, h, w, 3] BGR in [0, 255] (fp32, or uint8 as cv2.imwrite would store it)."""
         self._require_ready()
         if kind == 0:
             N, _, H, W = frame.shape
         else:
             N, H, W, _ = frame.shape
         h = self._vgg("Encoder", frame.contiguous(), kind, True, N, H, W, "content", norm0=self.stats["norm0"])
-        return self._decode(h, out)
+        return self._decode(h, out, post)
 
     @torch.no_grad()
     def encode(self, frame, kind=0):
@@ -465,7 +497,30 @@ class StyleEngine:
         x = f_content.permute(0, 2, 3, 1).contiguous()
         return self._decode(self._pointwise(x, make_epilogue(norm1=self.stats["norm0"])), out)
 
-    def _decode(self, h, out=None):
+    def _head(self, h, out=None, post=None):
+        """Decoder.slice1 (:341, :450); ``post`` as in forward()."""
+        head = self.w["slice1"]
+        if post is None:
+            return self._conv(head, h, make_epilogue(bias=head.bias), L.OUT_F32_NCHW, out=out, out_C=3)
+        mode, crop = post
+        if mode not in ("f32", "u8"):
+            raise ValueError("post mode must be 'f32' or 'u8'")
+        if self._impl_for(head) != L.IMPL_TCGEN05:      # bring-up path: separate postprocess kernel
+            y = self._conv(head, h, make_epilogue(bias=head.bias), L.OUT_F32_NCHW, out_C=3)
+            return self.postprocess(y, crop, mode, out)
+        return self._conv(head, h, make_epilogue(bias=head.bias), L.OUT_BGR_U8 if mode == "u8" else L.OUT_BGR_F32, out=out, crop=crop)
+
+    def postprocess(self, y, crop=None, mode="f32", out=None):
+        """transform_back_image + tensor2numpy (test/framework.py:39-49) + crop on an fp32 NCHW network output."""
+        N, _, H, W = y.shape
+        y0, x0, h, w = crop if crop is not None else (0, 0, H, W)
+        dt = torch.uint8 if mode == "u8" else torch.float32
+        out = out if out is not None else torch.empty((N, h, w, 3), dtype=dt, device=self.device)
+        fn = self.lib.rrv_postprocess_bgr_u8 if mode == "u8" else self.lib.rrv_postprocess_bgr
+        L.check(fn(y.contiguous().data_ptr(), N, H, W, y0, x0, h, w, out.data_ptr(), L.stream()), "rrv_postprocess_bgr")
+        return out
+
+    def _decode(self, h, out=None, post=None):
         """norm[0](relu4_1) planes -> Filter1..3 -> AdaIN -> slice4..2 -> slice1 (Decoder.forward :441-451)."""
         st, tabs = self.stats, self.style["tabs"]
         for i, f in enumerate(FILTERS):
@@ -481,17 +536,16 @@ class StyleEngine:
             y = self._conv(bw["conv1"], h, make_epilogue(bias=bw["conv1"].bias, act=2, norm1=st[block + ".norm1"]))
             h = self._conv(bw["conv2"], y, make_epilogue(bias=bw["conv2"].bias, act=2, norm1=st[block + ".norm2"],
                                                         res=s, res_shift=1, norm2=st[nxt], affine=tabs[lvl]))
-        head = self.w["slice1"]
-        return self._conv(head, h, make_epilogue(bias=head.bias), L.OUT_F32_NCHW, out=out, out_C=3)
+        return self._head(h, out, post)
 
     @torch.no_grad()
-    def forward_graphed(self, frame, kind=0):
+    def forward_graphed(self, frame, kind=0, post=None):
         """forward() replayed from a CUDA graph: the ~30 launches of a frame (with their TMA descriptors baked
         in) are captured once per input shape and clip state, then each call is one D2D copy of the frame into
         the graph's static input plus one graph launch.  Returns the graph's static output tensor (valid until
         the next call).  Any change of weights, style or clip statistics drops the captured graphs."""
         self._require_ready()
-        key = ("graph", kind, tuple(frame.shape), frame.dtype)
+        key = ("graph", kind, tuple(frame.shape), frame.dtype, post)
         plan = self._plans.get(key)
         if plan is None:
             if kind == 0:
@@ -500,16 +554,25 @@ class StyleEngine:
                 N, H, W, _ = frame.shape
             g_in = torch.empty_like(frame, memory_format=torch.contiguous_format)
             g_in.copy_(frame)
-            g_out = torch.empty((N, 3, H, W), dtype=torch.float32, device=self.device)
+            oh, ow = self.output_size(H, W)
+            if post is None:
+                g_out = torch.empty((N, 3, oh, ow), dtype=torch.float32, device=self.device)
+            else:
+                crop = post[1] if post[1] is not None else (0, 0, oh, ow)
+                g_out = torch.empty((N, crop[2], crop[3], 3), dtype=torch.uint8 if post[0] == "u8" else torch.float32, device=self.device)
             n0 = self.lib.rrv_launch_count()
-            self.forward(g_in, kind, out=g_out)                     # eager warm-up: function attributes, allocator pools
+            self.forward(g_in, kind, out=g_out, post=post)          # eager warm-up: function attributes, allocator pools
             launches = self.lib.rrv_launch_count() - n0
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                self.forward(g_in, kind, out=g_out)
+                self.forward(g_in, kind, out=g_out, post=post)
             plan = (graph, g_in, g_out, launches)
             self._plans[key] = plan
+            while len(self._plans) > self.MAX_PLANS:        # each plan pins a private pool with a frame's activations
+                self._plans.popitem(last=False)
+        else:
+            self._plans.move_to_end(key)
         graph, g_in, g_out, launches = plan
         g_in.copy_(frame, non_blocking=True)
         graph.replay()
@@ -550,7 +613,7 @@ class StyleEngine:
         else:
             N, H, W, _ = frame.shape
         frame = frame.contiguous()
-        out = torch.empty((N, 3, H, W), dtype=torch.float32, device=self.device)
+        out = torch.empty((N, 3) + self.output_size(H, W), dtype=torch.float32, device=self.device)
         tabs = self.style["tabs"]
         for i in range(N):
             x = self._vgg("Encoder", frame[i:i + 1], kind, gray, 1, H, W, "raw")              # fp32 NHWC relu4_1
@@ -583,8 +646,7 @@ class StyleEngine:
                 del r2
                 h = self._pointwise(r, make_epilogue(norm1=self._frame_norm(r), affine=tabs[lvl]))    # Decoder.AdaIN :311-319
                 del r
-            head = self.w["slice1"]
-            self._conv(head, h, make_epilogue(bias=head.bias), L.OUT_F32_NCHW, out=out[i:i + 1], out_C=3)
+            self._head(h, out[i:i + 1])
         return out
 
     def _folded(self, f, wf1, wf2):
@@ -633,4 +695,4 @@ class StyleEngine:
         self.stats = {k: v.to(self.device).contiguous() for k, v in state["stats"].items()}
         for f, (a, b) in state["filters"].items():
             self._fold_filter(f, a.to(self.device), b.to(self.device))
-        self._plans = {}
+        self._plans = OrderedDict()

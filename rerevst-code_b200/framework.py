@@ -37,6 +37,8 @@ class Stylization:
             raise ValueError("expected a uint8 HxWx3 BGR image (cv2.imread layout)")
         key = img.shape
         if key not in self._pin:
+            while len(self._pin) >= 4:          # bounded: streams of varying resolution do not grow pinned memory forever
+                self._pin.pop(next(iter(self._pin)))
             self._pin[key] = (torch.empty((1,) + key, dtype=torch.uint8).pin_memory(), torch.cuda.Event())
         pinned, copied = self._pin[key]
         copied.synchronize()                    # the previous asynchronous upload from this staging buffer has finished
@@ -70,13 +72,21 @@ class Stylization:
             del self.model.Vgg19
             self.model.have_delete_vgg = True
 
-    def transfer(self, frame, crop=None):
+    def transfer(self, frame, crop=None, out_dtype="f32"):
         """frame: uint8 BGR HWC -> float32 BGR HWC in [0,255] (test/framework.py:106-118).
-        crop=(y0, x0, h, w) additionally applies generate_real_video.py:167 on the device."""
-        out = self.transfer_device(frame, crop)
+        crop=(y0, x0, h, w) additionally applies generate_real_video.py:167 on the device.
+        out_dtype="u8" returns the frame rounded to uint8 the way cv2.imwrite stores a float32 image (:170): a quarter of
+        the bytes to download."""
+        out = self.transfer_device(frame, crop, out_dtype)
         return out.cpu().numpy()[0]
 
-    def transfer_stream(self, frames, crop=None, depth=3, pad_to=None, copy=True):
+    @staticmethod
+    def output_size(H, W):
+        """Size of the stylized frame for an H x W input: (H // 8) * 8 x (W // 8) * 8 (three floor max-pools, three x2
+        upsamples), e.g. 436 x 1024 -> 432 x 1024 exactly like the reference."""
+        return (H // 8) * 8, (W // 8) * 8
+
+    def transfer_stream(self, frames, crop=None, depth=3, pad_to=None, copy=True, out_dtype="f32"):
         """Generator over an iterable of uint8 BGR frames of one size: yields exactly what
         ``transfer(frame, crop)`` returns for each, in order, but pipelined -- the pinned-memory
         upload of frame i+1 (copy-in stream) and the download of frame i-1 (copy-out stream) overlap the
@@ -87,7 +97,12 @@ class Stylization:
         copy per 1080p frame, which is what limits 8 processes sharing one host).
 
         ``pad_to=(PH, PW)``: the frames are RAW; ReshapeTool.process (generate_real_video.py:66-83, reflect border of 64
-        pixels up to PH x PW) runs on the device, and ``crop`` defaults to the raw frame's window (:167)."""
+        pixels up to PH x PW) runs on the device, and ``crop`` defaults to the raw frame's window (:167).
+
+        ``out_dtype="u8"``: uint8 frames (see transfer): 6.2 MB instead of 24.9 MB per 1080p frame over PCIe."""
+        if out_dtype not in ("f32", "u8"):
+            raise ValueError("out_dtype must be 'f32' or 'u8'")
+        t_out = torch.uint8 if out_dtype == "u8" else torch.float32
         eng = self.model._eng()
         cur = torch.cuda.current_stream(self.device)
         s_in, s_out = self._side_streams()
@@ -104,19 +119,22 @@ class Stylization:
                 raise ValueError("expected a uint8 HxWx3 BGR image (cv2.imread layout)")
             rH, rW = frame.shape[:2]                       # as uploaded
             H, W = pad_to if pad_to is not None else (rH, rW)      # as seen by the network
+            oH, oW = self.output_size(H, W)                         # as returned by it
             if crop is not None:
                 y0, x0, h, w = crop
             elif pad_to is not None:
                 y0, x0, h, w = 64, 64, rH, rW
             else:
-                y0, x0, h, w = 0, 0, H, W
+                y0, x0, h, w = 0, 0, oH, oW
+            if y0 < 0 or x0 < 0 or y0 + h > oH or x0 + w > oW:
+                raise ValueError(f"crop {(y0, x0, h, w)} outside the {oH}x{oW} stylized frame")
             if len(slots) < depth:
                 slots.append(dict(host_in=torch.empty((1, rH, rW, 3), dtype=torch.uint8).pin_memory(),
                                   dev_in=torch.empty((1, rH, rW, 3), dtype=torch.uint8, device=self.device),
                                   dev_pad=(torch.empty((1, H, W, 3), dtype=torch.uint8, device=self.device)
                                            if pad_to is not None else None),
-                                  dev_out=torch.empty((1, h, w, 3), dtype=torch.float32, device=self.device),
-                                  host_out=torch.empty((1, h, w, 3), dtype=torch.float32).pin_memory(),
+                                  dev_out=torch.empty((1, h, w, 3), dtype=t_out, device=self.device),
+                                  host_out=torch.empty((1, h, w, 3), dtype=t_out).pin_memory(),
                                   ev_in=torch.cuda.Event(), ev_done=torch.cuda.Event(), ev_out=torch.cuda.Event(),
                                   ev_free=torch.cuda.Event()))
             slot = slots[i % depth]
@@ -130,15 +148,15 @@ class Stylization:
                 slot["dev_in"].copy_(slot["host_in"], non_blocking=True)
                 slot["ev_in"].record(s_in)
             cur.wait_event(slot["ev_in"])
-            cur.wait_event(slot["ev_out"])                  # dev_out of this slot has been downloaded
             net_in = slot["dev_in"]
             if pad_to is not None:
                 net_in = slot["dev_pad"]
                 L.check(L.lib().rrv_reflect_pad_u8(slot["dev_in"].data_ptr(), 1, rH, rW, 64, 64, H, W, net_in.data_ptr(), L.stream()),
                         "rrv_reflect_pad_u8")
-            net_out = self._net(eng, net_in)
-            L.check(L.lib().rrv_postprocess_bgr(net_out.data_ptr(), 1, H, W, y0, x0, h, w, slot["dev_out"].data_ptr(),
-                                                L.stream()), "rrv_postprocess_bgr")
+            cur.wait_event(slot["ev_out"])                  # dev_out of this slot has been downloaded
+            # the network's output is the captured graph's single static buffer: a device-to-device copy (~10 us at 1080p) into
+            # this slot's buffer lets the next frame's kernels start while this frame is still being downloaded
+            slot["dev_out"].copy_(self._net(eng, net_in, (out_dtype, (y0, x0, h, w))), non_blocking=True)
             slot["ev_free"].record(cur)
             slot["ev_done"].record(cur)
             with torch.cuda.stream(s_out):
@@ -149,23 +167,27 @@ class Stylization:
         while pending:
             yield finish(pending.pop(0))
 
-    def _net(self, eng, dev_u8):
-        """uint8 NHWC frame on the device -> fp32 NCHW network output (global mode: one CUDA-graph replay)."""
+    def _net(self, eng, dev_u8, post):
+        """uint8 NHWC frame on the device -> the finished [N, h, w, 3] BGR frame on the device.  Global mode: one CUDA-graph
+        replay whose last kernel (the RGB head) also de-normalises, clamps, crops and converts; the returned tensor is the
+        graph's static output, valid until the next call."""
         if self.use_Global:
-            return eng.forward_graphed(dev_u8, kind=1)
-        return eng.forward_frame(dev_u8, kind=1, gray=True)
+            return eng.forward_graphed(dev_u8, kind=1, post=post)
+        y = eng.forward_frame(dev_u8, kind=1, gray=True)
+        return eng.postprocess(y, post[1], post[0])
 
     def _side_streams(self):
         if not hasattr(self, "_streams"):
             self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         return self._streams
 
-    def transfer_device(self, frame, crop=None):
+    def transfer_device(self, frame, crop=None, out_dtype="f32"):
+        if out_dtype not in ("f32", "u8"):
+            raise ValueError("out_dtype must be 'f32' or 'u8'")
         eng = self.model._eng()
-        y = self._net(eng, self._upload(frame))
-        N, _, H, W = y.shape
-        y0, x0, h, w = crop if crop is not None else (0, 0, H, W)
-        out = torch.empty((N, h, w, 3), dtype=torch.float32, device=self.device)
-        L.check(L.lib().rrv_postprocess_bgr(y.data_ptr(), N, H, W, y0, x0, h, w, out.data_ptr(), L.stream()),
-                "rrv_postprocess_bgr")
-        return out
+        dev = self._upload(frame)
+        oH, oW = self.output_size(dev.shape[1], dev.shape[2])
+        crop = tuple(crop) if crop is not None else (0, 0, oH, oW)
+        if crop[0] < 0 or crop[1] < 0 or crop[0] + crop[2] > oH or crop[1] + crop[3] > oW:
+            raise ValueError(f"crop {crop} outside the {oH}x{oW} stylized frame")
+        return self._net(eng, dev, (out_dtype, crop)).clone()       # the graph's static output is reused by the next call

@@ -34,8 +34,8 @@ class _Warp(torch.autograd.Function):
     def backward(ctx, grad_out):
         (flo,) = ctx.saved_tensors
         B, C, H, W = grad_out.shape
-        gx = torch.zeros_like(grad_out)
         grad_out = grad_out.contiguous()
+        gx = torch.zeros(grad_out.shape, dtype=grad_out.dtype, device=grad_out.device)     # contiguous NCHW like the kernel writes
         L.check(L.lib().rrv_warp_backward(grad_out.data_ptr(), flo.data_ptr(), B, C, H, W, gx.data_ptr(),
                                           L.stream()), "rrv_warp_backward")
         return gx, None
@@ -114,6 +114,11 @@ class TemporalLoss(torch.nn.Module):
             w = warp(first_frame, forward_flow)
             return torch.mean(torch.abs(w - second_frame)), w
         B, C, H, W = _check(first_frame, forward_flow)
+        if not second_frame.is_cuda or second_frame.dtype != torch.float32 or second_frame.shape != first_frame.shape:
+            # the fused kernel reads second_frame element for element: anything else takes the reference's own route
+            # (broadcasting / dtype promotion / the usual PyTorch errors)
+            w = warp(first_frame, forward_flow)
+            return torch.mean(torch.abs(w - second_frame)), w
         first, second, flo = first_frame.contiguous(), second_frame.contiguous(), forward_flow.contiguous()
         warped = torch.empty_like(first)
         acc = torch.empty(1, dtype=torch.float64, device=first.device)

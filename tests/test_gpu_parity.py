@@ -713,3 +713,194 @@ def test_generate_real_video_entry(tmp_path, dev, state_dict):
         got = cv2.imread(os.path.join(out_dir, os.path.basename(path))).astype(np.float32)
         assert got.shape == ref.shape
         assert float(np.max(np.abs(got - np.clip(np.rint(ref), 0, 255)))) <= 1.0
+
+
+# ---------------------------------------------------------------------------------- round 2: sizes / paths the bench times
+
+def _oracle_from_engine(state_dict, eng):
+    import bench
+    return bench.oracle_from_engine(state_dict, eng)
+
+
+def test_frame_mode_ragged_270x480_against_oracle(L, dev, state_dict):
+    """Frame mode (use_Global=False) on a frame that is no multiple of 8 rows (270 -> 33.75 at 1/8 scale): per-frame
+    statistics, per-frame filters, output 264 x 480 like the reference (three floor pools, three x2 upsamples)."""
+    import bench
+    from oracle import stylenet
+    from rerevst_code_b200.framework import Stylization
+    style, frame = bench.synthetic_frame(96, 128, 3), bench.synthetic_frame(270, 480, 4)
+    fw = Stylization(state_dict, cuda=True, use_Global=False)
+    fw.prepare_style(style)
+    got = fw.transfer(frame)
+    fs = stylenet.encoder_style(stylenet.transform_image(stylenet.numpy2tensor(style)), state_dict)
+    ref = stylenet.frame_mode_forward(state_dict, stylenet.transform_image(stylenet.numpy2tensor(frame)), fs)
+    ref = stylenet.tensor2numpy(stylenet.transform_back_image(ref))
+    assert got.shape == ref.shape == (264, 480, 3)
+    assert float(np.abs(got - ref).max()) < 255 * TOL
+    u8 = fw.transfer(frame, out_dtype="u8")
+    assert u8.dtype == np.uint8 and np.array_equal(u8, np.rint(got).astype(np.uint8))
+
+
+def test_prepass_8_samples_540x960_against_oracle(L, dev, state_dict):
+    """Decoder.compute (style_network_global.py:425-439) at a realistic size: 8 sampled frames of 540 x 960 (ragged at 1/8
+    scale: 67.5 x 120), all 11 statistic tables and 6 dynamic filters against the CPU oracle's own pre-pass (~20 s of CPU)."""
+    import bench
+    from oracle import stylenet
+    from rerevst_code_b200.framework import Stylization
+    torch.set_num_threads(os.cpu_count() or 1)
+    style = bench.synthetic_frame(256, 320, 1)
+    frames = [bench.synthetic_frame(540, 960, 60 + i) for i in range(8)]
+    fw = Stylization(state_dict, cuda=True)
+    fw.prepare_style(style)
+    fw.clean()
+    for f in frames:
+        fw.add(f)
+    fw.compute()
+    eng = fw.model._eng()
+    o = stylenet.GlobalOracle(state_dict)
+    o.generate_style_features(stylenet.transform_image(stylenet.numpy2tensor(style)))
+    o.clean()
+    for f in frames:
+        o.add(stylenet.transform_image(stylenet.numpy2tensor(f)))
+    o.compute()
+    for k, st in o.clip.stats.items():
+        got = eng.stats[k].cpu().numpy()
+        for r in range(4):
+            assert rel_linf(got[r], st[r].reshape(-1).numpy()) < TOL, (k, r)
+    for f, (a, b) in o.clip.filters.items():
+        assert rel_linf(eng.filters[f][0].cpu().numpy(), a.reshape(32, 32).numpy()) < TOL, f
+        assert rel_linf(eng.filters[f][1].cpu().numpy(), b.reshape(32, 32).numpy()) < TOL, f
+    # and a frame through both with their OWN pre-pass results: the whole script path at this size
+    frame = bench.synthetic_frame(540, 960, 99)
+    assert float(np.abs(fw.transfer(frame) - o.transfer(frame)).max()) < 255 * TOL
+
+
+def test_non_multiple_of_8_frame_436x1024(L, dev, state_dict):
+    """A raw Sintel-sized frame (test/inputs/ambush_4: 436 x 1024): the reference returns 432 x 1024; every entry point
+    (eager forward, graph replay, transfer, transfer_stream, fused u8 head) must agree with the oracle on that shape."""
+    import bench
+    from rerevst_code_b200.framework import Stylization
+    fw = Stylization(state_dict, cuda=True)
+    fw.prepare_style(bench.synthetic_frame(128, 160, 1))
+    fw.clean()
+    for i in range(2):
+        fw.add(bench.synthetic_frame(218, 512, 70 + i))
+    fw.compute()
+    eng = fw.model._eng()
+    frame = bench.synthetic_frame(436, 1024, 71)
+    o = _oracle_from_engine(state_dict, eng)
+    ref = o.transfer(frame)
+    assert ref.shape == (432, 1024, 3)
+    d = torch.from_numpy(frame).unsqueeze(0).to(dev)
+    y = eng.forward(d, kind=1)
+    assert tuple(y.shape) == (1, 3, 432, 1024)
+    yg = eng.forward_graphed(d, kind=1)
+    assert tuple(yg.shape) == (1, 3, 432, 1024) and torch.equal(yg, y)
+    got = fw.transfer(frame)
+    assert got.shape == ref.shape and float(np.abs(got - ref).max()) < 255 * TOL
+    st = list(fw.transfer_stream(iter([frame, frame[:, ::-1].copy(), frame])))
+    assert all(s.shape == ref.shape for s in st) and np.array_equal(st[0], got) and np.array_equal(st[2], got)
+    with pytest.raises(ValueError):
+        fw.transfer(frame, crop=(0, 0, 436, 1024))                     # the window must lie inside the 432 x 1024 result
+    with pytest.raises(ValueError):
+        eng.forward(d, kind=1, out=torch.empty((1, 3, 436, 1024), device=dev))
+
+
+def test_head_fused_postprocess_and_u8(L, dev, state_dict):
+    """The RGB head writing the finished frame (RRV_OUT_BGR_F32 / _U8: transform_back_image + tensor2numpy + crop in the epilogue)
+    against the separate rrv_postprocess_bgr kernel on the head's NCHW output: bit-equal; uint8 = rint of the float frame."""
+    import bench
+    from rerevst_code_b200.framework import Stylization
+    fw = Stylization(state_dict, cuda=True)
+    fw.prepare_style(bench.synthetic_frame(96, 96, 1))
+    fw.clean()
+    fw.add(bench.synthetic_frame(64, 96, 2))
+    fw.compute()
+    eng = fw.model._eng()
+    d = torch.from_numpy(bench.synthetic_frame(104, 200, 3)).unsqueeze(0).to(dev)
+    y = eng.forward(d, kind=1)
+    for crop in (None, (8, 24, 80, 150), (0, 0, 1, 1), (103, 199, 1, 1)):
+        want = eng.postprocess(y, crop, "f32")
+        got = eng.forward(d, kind=1, post=("f32", crop))
+        assert got.dtype == torch.float32 and torch.equal(got, want), crop
+        u8 = eng.forward(d, kind=1, post=("u8", crop))
+        assert u8.dtype == torch.uint8 and torch.equal(u8, torch.round(want).to(torch.uint8)), crop
+        assert torch.equal(eng.postprocess(y, crop, "u8"), u8)
+        assert torch.equal(eng.forward_graphed(d, kind=1, post=("u8", crop)), u8)
+    assert float(want.min()) >= 0.0 and float(want.max()) <= 255.0
+
+
+def test_conv_operand_terms_knob(L, dev):
+    """rrv_conv.terms: NO_WLO multiplies full activations by bf16-rounded weights, NO_ALO bf16-rounded activations by full
+    weights (two MMAs per k-slice instead of three); each must match exactly that arithmetic on the CPU."""
+    from rerevst_code_b200.engine import ConvW, make_epilogue
+    if len(_impls(L)) < 2:
+        pytest.skip("tcgen05 path not built")
+    g = torch.Generator().manual_seed(77)
+    bf = lambda t: t.to(torch.bfloat16).float()
+    two = lambda t: bf(t) + bf(t - bf(t))
+    for (N, H, W, Cin, Cout, k) in ((1, 24, 70, 64, 64, 3), (1, 20, 24, 512, 64, 3), (2, 16, 16, 128, 256, 3)):
+        x = torch.randn(N, Cin, H, W, generator=g)
+        w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+        cw = ConvW(w.to(dev), None)
+        xp = _to_planes(L, x.to(dev))
+        refs = {L.TERMS_FULL: F.conv2d(two(x), two(w), padding=1), L.TERMS_NO_WLO: F.conv2d(two(x), bf(w), padding=1),
+                L.TERMS_NO_ALO: F.conv2d(bf(x), two(w), padding=1)}
+        outs = {}
+        for terms, ref in refs.items():
+            d = L.Conv()
+            d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = N, H, W, Cin, Cout, k, 0
+            d.in_hi, d.in_lo = L.ptr(xp.hi), L.ptr(xp.lo)
+            d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
+            d.ep = make_epilogue()
+            d.out_mode = L.OUT_F32_NHWC
+            d.terms = terms
+            out = torch.empty((N, H, W, Cout), dtype=torch.float32, device=dev)
+            d.out_f32 = out.data_ptr()
+            L.check(L.lib().rrv_conv2d(C.byref(d), L.IMPL_TCGEN05, L.stream()))
+            outs[terms] = out.permute(0, 3, 1, 2).cpu()
+            assert rel_linf(outs[terms], ref) < 3e-5, (terms, Cin, Cout)
+        assert rel_linf(outs[L.TERMS_NO_WLO], refs[L.TERMS_FULL]) > 1e-4          # the dropped term is really dropped
+
+
+def test_temporal_loss_config5_512_b4(dev):
+    """BASELINE.json configs[4]: B = 4 pairs at 512 x 512, the flow of GenerateFakeFlow (train/loss_networks.py:71-86) under
+    fixed seeds; warp bit-equal to the oracle, loss within 1e-6; GenerateFakeData (:88-104) = warp + N(0, sigma in [1e-3, 2e-3])."""
+    import random
+    from oracle import warp as ow
+    from rerevst_code_b200.loss_networks import TemporalLoss, warp, warp_indices
+    B, Cc, H, W = 4, 3, 512, 512
+    g = torch.Generator().manual_seed(5)
+    first = torch.randn(B, Cc, H, W, generator=g)
+    tl = TemporalLoss()
+    np.random.seed(0)
+    random.seed(0)
+    flow = tl.GenerateFakeFlow(H, W)
+    assert tuple(flow.shape) == (2, H, W) and float(flow.abs().max()) < 40.0
+    flow_b = flow.unsqueeze(0).expand(B, 2, H, W).contiguous()
+    iy, ix = ow.warp_indices(flow_b.numpy())
+    idx = warp_indices(flow_b.to(dev)).cpu().numpy()
+    assert np.array_equal(idx[..., 0], iy) and np.array_equal(idx[..., 1], ix)
+    ref_w = ow.warp(first.numpy(), flow_b.numpy())
+    second = torch.from_numpy(ref_w) + 1.5e-3 * torch.randn(B, Cc, H, W, generator=g)
+    loss, warped = tl(first.to(dev), second.to(dev), flow_b.to(dev))
+    assert np.array_equal(warped.cpu().numpy(), ref_w)
+    ref_loss = float(np.mean(np.abs(ref_w.astype(np.float64) - second.numpy().astype(np.float64))))
+    assert abs(float(loss) - ref_loss) <= 1e-6 * ref_loss
+    # GenerateFakeData: same seeds -> same flow; second = warp(first, flow) + Gaussian noise of sigma in [noise_level, 2 noise_level)
+    np.random.seed(0)
+    random.seed(0)
+    sec, fl2 = tl.GenerateFakeData(first.to(dev))
+    assert tuple(fl2.shape) == (B, 2, H, W) and torch.equal(fl2[0].cpu(), flow) and torch.equal(fl2[3].cpu(), flow)
+    noise = (sec - warp(first.to(dev), fl2)).cpu()
+    assert 0.9e-3 < float(noise.std()) < 2.1e-3 and abs(float(noise.mean())) < 1e-5
+    # a CPU / mis-shaped second frame must not reach the fused kernel (ADVICE r1): the reference's own route is taken
+    l2, _ = tl(first.to(dev), second[:, :1].to(dev), flow_b.to(dev))           # broadcasts like torch
+    assert torch.isfinite(l2)
+    # non-contiguous upstream gradient (channels_last): the returned gradient is in the logical NCHW order
+    x = first.to(dev).requires_grad_(True)
+    go = torch.randn(B, Cc, H, W, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+    warp(x, flow_b.to(dev)).backward(go)
+    x2 = first.to(dev).requires_grad_(True)
+    warp(x2, flow_b.to(dev)).backward(go.contiguous())
+    assert torch.equal(x.grad, x2.grad)

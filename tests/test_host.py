@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in _header_functions():
         assert hasattr(handle, name), name
-    assert _lib.lib().rrv_abi_version() == 1
+    assert _lib.lib().rrv_abi_version() == _lib.ABI_VERSION == 2
     assert _lib.lib().rrv_launch_count() == 0
 
 
@@ -100,7 +100,10 @@ def test_product_never_imports_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in text.replace("the oracle, ", "").lower() or f == "framework.py", (dirpath, f)
+                # no import / dynamic import / path reference of the oracle package anywhere in the product (prose may name it)
+                bad = re.findall(r"^\s*(?:from|import)\s+oracle\b|import_module\(\s*[\"']oracle|__import__\(\s*[\"']oracle|[\"'/]oracle/",
+                                 text, flags=re.M)
+                assert not bad, (dirpath, f, bad)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/train"), reason="reference not present")
