@@ -326,6 +326,36 @@ def run_config5(sd, dev):
                     "launch-latency bound; kernel-only times are in profiles/)"}
 
 
+def run_frame_mode(sd, dev, precision, kernels, pk, check):
+    """use_Global=False (test/style_network_frame.py): per-frame statistics and per-frame dynamic filters, 1080p
+    padded, device-resident uint8 frames, one CUDA-graph replay per frame; parity of the replayed output on the full frame."""
+    from oracle import stylenet
+    from rerevst_code_b200.framework import Stylization
+    h, w = SIZES["1080p"]
+    ph, pw = padded_size(h, w)
+    style = synthetic_frame(512, 512, 1)
+    fw = Stylization(sd, cuda=True, use_Global=False, precision=precision, impl=kernels)
+    eng = fw.model._eng()
+    fw.prepare_style(style)
+    host = [reflect_pad(synthetic_frame(h, w, 500 + i), ph, pw) for i in range(2)]
+    devf = [torch.from_numpy(f).unsqueeze(0).to(dev) for f in host]
+    steps = 30
+    ms = device_timer(lambda i: eng.forward_frame_graphed(devf[i % 2], kind=1), steps, 4)
+    out = {"value": steps / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms / steps, "steps": steps, "padded": [ph, pw],
+           "whole_frame_roofline_frac_burst": flops_per_frame(ph, pw) * steps / (ms * 1e-3) / 1e12 / pk["burst"],
+           "launch": "one CUDA graph per frame: statistics from the producing kernels' epilogues, filters folded by rrv_fold_filter"}
+    if check:
+        got = eng.forward_frame_graphed(devf[(steps - 1) % 2], kind=1).cpu()
+        fs = stylenet.encoder_style(stylenet.transform_image(stylenet.numpy2tensor(style)), {k: v.float() for k, v in sd.items()})
+        ref = stylenet.frame_mode_forward({k: v.float() for k, v in sd.items()},
+                                          stylenet.transform_image(stylenet.numpy2tensor(host[(steps - 1) % 2])), fs)
+        out["parity_rel_linf_graph_replay_vs_cpu_oracle"] = float((got - ref).abs().max() / ref.abs().max())
+        out["tolerance"] = TOL
+    del fw, eng, devf
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_gpu_baseline(sd, eng, dev, frame_u8, crop, steps):
     """The reference's own GPU route: eager PyTorch ops on this device (cuDNN convolutions, cudnn.benchmark=True as in
     test/framework.py:61-63), same weights / statistics / frame.  Strict fp32 and TF32-allowed (PyTorch's conv default)."""
@@ -467,6 +497,7 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     last = (args.steps - 1) % nfr
     graph_out = eng.forward_graphed(dev_frames[last], kind=1, post=post).cpu().numpy()[0] if rank == 0 else None   # = the last timed replay
+    raw_out = eng.forward_graphed(dev_frames[last], kind=1).cpu() if rank == 0 and not args.no_cpu_baseline else None   # TransformerNet.forward's own result
 
     # ---- end-to-end arm: host uint8 in, host frame out, every step (generate_real_video's loop: Stylization.transfer_stream,
     #      which overlaps the pinned H2D / D2H copies of neighbouring frames with the kernels) ----
@@ -605,15 +636,19 @@ def main():
         torch.set_num_threads(cores)
         o = oracle_from_engine(sd, eng)
         t0 = time.perf_counter()
-        ref = oracle_frame(o, host_frames[last], crop)
+        from oracle import stylenet
+        ref_raw = o.forward(stylenet.transform_image(stylenet.numpy2tensor(host_frames[last])))
         dt = time.perf_counter() - t0
+        ref = stylenet.tensor2numpy(stylenet.transform_back_image(ref_raw))[crop[0]:crop[0] + crop[2], crop[1]:crop[1] + crop[3]]
         parity = {"tolerance": TOL if args.precision == "x3" else None,
+                  "raw_nchw_graph_replay_vs_cpu_oracle": float((raw_out - ref_raw).abs().max() / ref_raw.abs().max()),
                   "graph_replay_vs_cpu_oracle": frame_err(graph_out, ref),
                   "transfer_stream_f32_vs_cpu_oracle": frame_err(kept["f32"], ref),
                   "transfer_stream_u8_equals_rint_of_oracle": float(np.mean(kept["u8"] == np.rint(ref).astype(np.uint8))),
                   "transfer_stream_u8_max_abs_diff": int(np.abs(kept["u8"].astype(np.int32) - np.rint(ref).astype(np.int32)).max()),
                   "what": f"frame {last} of the rotation = the last timed step of every arm, full {ph}x{pw} frame cropped to {h}x{w}; "
-                          "relative L-inf on the [0,255] BGR frame; the oracle takes the per-clip tables from the GPU pre-pass "
+                          "relative L-inf on the finished [0,255] BGR frame (raw_nchw: on TransformerNet.forward's unclamped result, the "
+                          "round-1 metric); the oracle takes the per-clip tables from the GPU pre-pass "
                           "(the pre-pass has its own parity tests, tests/test_gpu_parity.py)"}
         if nccl_parity is not None:
             parity["nccl_prepass_vs_single_process"] = nccl_parity
@@ -655,6 +690,10 @@ def main():
             line["config5_temporal"] = run_config5(sd, dev)
         except Exception as e:
             line["config5_temporal"] = {"error": repr(e)}
+        try:
+            line["frame_mode"] = run_frame_mode(sd, dev, args.precision, args.kernels, pk, not args.no_cpu_baseline)
+        except Exception as e:
+            line["frame_mode"] = {"error": repr(e)}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.barrier()

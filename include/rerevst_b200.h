@@ -99,6 +99,12 @@ typedef struct rrv_conv {
     int32_t terms;          /* RRV_TERMS_* (tcgen05 path with lo planes) */
     void*   out_img;        /* RRV_OUT_BGR_*: [N][crop_h][crop_w][3] fp32 or uint8 */
     int32_t crop_y0, crop_x0, crop_h, crop_w;   /* RRV_OUT_BGR_*: window of the H x W result that is kept */
+    double* stats;          /* optional double[5][Cout] = {count, sum, sum of squares, min, max} of the values this convolution
+                             * WRITES, accumulated by its epilogue (atomics; initialise with rrv_stats_init, convert with
+                             * rrv_stats_sums_to_m2): the statistics of the InstanceNorm that follows (style_network_frame.py:39-43,
+                             * style_network_global.py:59-77) without another pass over the tensor.  tcgen05 path, epilogue of
+                             * bias + activation only, not with pool. */
+    int32_t stats_minmax;   /* 0: rows 3, 4 are left alone (frame mode has no clamp); 1: min / max as well (pre-pass) */
 } rrv_conv;
 
 int rrv_conv2d(const rrv_conv* p, int impl, void* stream);
@@ -119,6 +125,13 @@ int rrv_tc_tune_pair(int enable, int min_bn);
 /* Merge the three dy taps of a 3x3 convolution into one MMA along N (N = 3 Cout) when 3 Cout <= 256: the
  * 64-channel layers, whose cost is the A-operand fetch.  Enabled by default. */
 int rrv_tc_tune_merge(int enable);
+/* KernelFilter fold (apply_filter, style_network_global.py:194-217; per frame in test/style_network_frame.py:97-105): the two
+ * predicted 32x32 matrices wf1, wf2 ([out][in], fp32) are multiplied into the filter's down_sample (512 -> 32) and upsample
+ * (32 -> 512) 3x3 weights (PyTorch OIHW fp32) and written as tensor-core blobs: down_blob = rrv_tc_weight_bytes(512, 64, 3, 0)
+ * bytes for a 512 -> 64 convolution (outputs 32..63 zero) with down_bias[64] = wf1 . down_b; up_blob =
+ * rrv_tc_weight_bytes(64, 512, 3, 0) bytes for a 64 -> 512 convolution (inputs 32..63 zero: use Cin_used = 32). */
+int rrv_fold_filter(const float* wf1, const float* wf2, const float* down_w, const float* down_b, const float* up_w,
+                    void* down_blob, float* down_bias, void* up_blob, void* stream);
 /* fp32 [Cout][Cin][k][k] -> [k*k][Cin_pad][Cout_pad] fp32 (zero padded) for the FFMA path. */
 int rrv_pack_weights_f32(const float* w_oihw, int Cin, int Cout, int ksize, int Cin_pad, int Cout_pad,
                          float* out, void* stream);
@@ -146,6 +159,11 @@ int rrv_maxpool2x2(const void* in_hi, const void* in_lo, int N, int H, int W, in
 int rrv_pointwise(const float* in, int64_t in_batch_stride, int N, int H, int W, int C,
                   const rrv_epilogue* ep, int out_mode, void* out_hi, void* out_lo, float* out_f32,
                   void* stream);
+/* Same, and the per-channel {sum, sum of squares[, min, max]} of the values written go into `stats` (see rrv_stats_init):
+ * the statistics of the NEXT normalisation come out of the pass that applies the previous one. */
+int rrv_pointwise_stats(const float* in, int64_t in_batch_stride, int N, int H, int W, int C,
+                        const rrv_epilogue* ep, int out_mode, void* out_hi, void* out_lo, float* out_f32,
+                        double* stats, int stats_minmax, void* stream);
 /* planes -> fp32 NCHW (debug / feature export) and fp32 NCHW -> planes. */
 int rrv_planes_to_nchw(const void* hi, const void* lo, int N, int H, int W, int C, float* out, void* stream);
 int rrv_nchw_to_planes(const float* in, int N, int H, int W, int C, void* hi, void* lo, void* stream);
@@ -168,6 +186,12 @@ int rrv_postprocess_bgr_u8(const float* in, int N, int H, int W, int y0, int x0,
  * data like InstanceNorm.compute (style_network_global.py:59-77).  Partials from several ranks
  * are merged on the device with rrv_stats_merge (Chan's parallel formula, fixed order). */
 int rrv_channel_stats(const float* x, int64_t npix, int C, double* part, void* stream);
+/* One-pass variant: a producing kernel (rrv_conv.stats, rrv_pointwise's stats argument) accumulates {sum, sum of squares,
+ * min, max} into a partial initialised by rrv_stats_init (count = number of pixels the producer will write); afterwards
+ * rrv_stats_sums_to_m2 turns row 2 into M2 about the mean, which makes it a partial like rrv_channel_stats' (mergeable,
+ * finalizable). */
+int rrv_stats_init(double* part, int C, double count, void* stream);
+int rrv_stats_sums_to_m2(double* part, int C, void* stream);
 int rrv_stats_merge(const double* parts, int nparts, int C, double* merged, void* stream);
 /* kind 0: saved-stat table float[4][C] = {mean, rsqrt(M2/n + eps), (min-mean)*rstd, (max-mean)*rstd}
  *         (InstanceNorm.compute, biased variance, eps 1e-8);

@@ -33,7 +33,7 @@ class Conv(C.Structure):
                 ("ups", _i32), ("in_hi", _vp), ("in_lo", _vp), ("w_f32", _vp), ("w_tc", _vp),
                 ("ep", Epilogue), ("out_mode", _i32), ("out_hi", _vp), ("out_lo", _vp), ("out_f32", _vp),
                 ("out_C", _i32), ("Cin_used", _i32), ("pool", _i32), ("terms", _i32), ("out_img", _vp),
-                ("crop_y0", _i32), ("crop_x0", _i32), ("crop_h", _i32), ("crop_w", _i32)]
+                ("crop_y0", _i32), ("crop_x0", _i32), ("crop_h", _i32), ("crop_w", _i32), ("stats", _vp), ("stats_minmax", _i32)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/rerevst_b200.h
@@ -51,6 +51,7 @@ SIGNATURES = {
     "rrv_tc_tune_pair": (C.c_int, [C.c_int, C.c_int]),
     "rrv_tc_tune_merge": (C.c_int, [C.c_int]),
     "rrv_pack_weights_f32": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "rrv_fold_filter": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rrv_first_layer": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rrv_maxpool2x2": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "rrv_pointwise": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), C.c_int,
@@ -61,6 +62,10 @@ SIGNATURES = {
     "rrv_postprocess_bgr": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rrv_postprocess_bgr_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rrv_channel_stats": (C.c_int, [_vp, _i64, C.c_int, _vp, _vp]),
+    "rrv_stats_init": (C.c_int, [_vp, C.c_int, C.c_double, _vp]),
+    "rrv_stats_sums_to_m2": (C.c_int, [_vp, C.c_int, _vp]),
+    "rrv_pointwise_stats": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), C.c_int,
+                                      _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "rrv_stats_merge": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp]),
     "rrv_stats_finalize": (C.c_int, [_vp, C.c_int, C.c_int, C.c_float, _vp, _vp]),
     "rrv_filter_fc": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),

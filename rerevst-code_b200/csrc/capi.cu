@@ -41,13 +41,17 @@ int first_layer(const void* src, int src_kind, int gray, int N, int H, int W, co
 int reflect_pad_u8(const void* src, int N, int H, int W, int top, int left, int PH, int PW, void* dst, cudaStream_t st);
 int maxpool2x2(const void* in_hi, const void* in_lo, int N, int H, int W, int C, void* out_hi, void* out_lo, cudaStream_t st);
 int pointwise(const float* in, long long in_bs, int N, int H, int W, int C, const rrv_epilogue* ep, int out_mode,
-              void* out_hi, void* out_lo, float* out_f32, cudaStream_t st);
+              void* out_hi, void* out_lo, float* out_f32, double* stats, int stats_minmax, cudaStream_t st);
 int planes_to_nchw(const void* hi, const void* lo, int N, int H, int W, int C, float* out, cudaStream_t st);
 int nchw_to_planes(const float* in, int N, int H, int W, int C, void* hi, void* lo, cudaStream_t st);
 int postprocess_bgr(const float* in, int N, int H, int W, int y0, int x0, int h, int w, float* out, cudaStream_t st);
 int postprocess_bgr_u8(const float* in, int N, int H, int W, int y0, int x0, int h, int w, uint8_t* out, cudaStream_t st);
 int pack_weights_f32(const float* w, int Cin, int Cout, int ksize, int Cin_pad, int Cout_pad, float* out, cudaStream_t st);
+int fold_filter(const float* wf1, const float* wf2, const float* down_w, const float* down_b, const float* up_w, void* down_blob,
+                float* down_bias, void* up_blob, cudaStream_t st);
 int channel_stats(const float* x, long long npix, int C, double* part, cudaStream_t st);
+int stats_init(double* part, int C, double count, cudaStream_t st);
+int stats_sums_to_m2(double* part, int C, cudaStream_t st);
 int stats_merge(const double* parts, int nparts, int C, double* merged, cudaStream_t st);
 int stats_finalize(const double* part, int C, int kind, float eps, float* out, cudaStream_t st);
 int filter_fc(const float* w, const float* b, const float* c_mean, const float* s_mean, float* out, cudaStream_t st);
@@ -91,6 +95,10 @@ int rrv_tc_tune_merge(int enable) { return tc_tune_merge(enable); }
 int rrv_pack_weights_f32(const float* w, int Cin, int Cout, int ksize, int Cin_pad, int Cout_pad, float* out, void* stream) {
     return pack_weights_f32(w, Cin, Cout, ksize, Cin_pad, Cout_pad, out, ST(stream));
 }
+int rrv_fold_filter(const float* wf1, const float* wf2, const float* down_w, const float* down_b, const float* up_w,
+                    void* down_blob, float* down_bias, void* up_blob, void* stream) {
+    return fold_filter(wf1, wf2, down_w, down_b, up_w, down_blob, down_bias, up_blob, ST(stream));
+}
 int rrv_first_layer(const void* src, int src_kind, int gray, int N, int H, int W, const float* w, const float* bias,
                     void* out_hi, void* out_lo, float* out_f32, void* stream) {
     return first_layer(src, src_kind, gray, N, H, W, w, bias, out_hi, out_lo, out_f32, ST(stream));
@@ -103,8 +111,15 @@ int rrv_maxpool2x2(const void* in_hi, const void* in_lo, int N, int H, int W, in
 }
 int rrv_pointwise(const float* in, int64_t in_bs, int N, int H, int W, int C, const rrv_epilogue* ep, int out_mode,
                   void* out_hi, void* out_lo, float* out_f32, void* stream) {
-    return pointwise(in, in_bs, N, H, W, C, ep, out_mode, out_hi, out_lo, out_f32, ST(stream));
+    return pointwise(in, in_bs, N, H, W, C, ep, out_mode, out_hi, out_lo, out_f32, nullptr, 0, ST(stream));
 }
+int rrv_pointwise_stats(const float* in, int64_t in_bs, int N, int H, int W, int C, const rrv_epilogue* ep, int out_mode,
+                        void* out_hi, void* out_lo, float* out_f32, double* stats, int stats_minmax, void* stream) {
+    RRV_REQUIRE(stats != nullptr, "rrv_pointwise_stats: stats is NULL");
+    return pointwise(in, in_bs, N, H, W, C, ep, out_mode, out_hi, out_lo, out_f32, stats, stats_minmax, ST(stream));
+}
+int rrv_stats_init(double* part, int C, double count, void* stream) { return stats_init(part, C, count, ST(stream)); }
+int rrv_stats_sums_to_m2(double* part, int C, void* stream) { return stats_sums_to_m2(part, C, ST(stream)); }
 int rrv_planes_to_nchw(const void* hi, const void* lo, int N, int H, int W, int C, float* out, void* stream) {
     return planes_to_nchw(hi, lo, N, H, W, C, out, ST(stream));
 }

@@ -177,6 +177,7 @@ int conv2d_ffma(const rrv_conv* p, cudaStream_t st) {
     }
     RRV_REQUIRE(p->Cout % 8 == 0, "rrv_conv2d: Cout must be < 8 or a multiple of 8 (got %d)", p->Cout);
     d.Cout_pad = (p->Cout + 63) / 64 * 64;
+    RRV_REQUIRE(p->stats == nullptr, "rrv_conv2d(ffma): fused statistics are a tensor-core path feature (use rrv_channel_stats)");
     RRV_REQUIRE(p->out_mode == RRV_OUT_PLANES || p->out_mode == RRV_OUT_F32_NHWC || p->out_mode == RRV_OUT_F32_NCHW,
                 "rrv_conv2d(ffma): out_mode %d is a tensor-core path feature (use rrv_postprocess_bgr after an NCHW output)", p->out_mode);
     if (p->out_mode == RRV_OUT_PLANES) RRV_REQUIRE(p->out_hi != nullptr, "rrv_conv2d: out_hi is NULL");

@@ -135,7 +135,7 @@ __device__ __forceinline__ void tap_offset(const TcParams& p, const TileCoord& c
 // Shared-memory table of the per-channel constants of the fused pointwise chain, one array of
 // Cout_pad floats per constant (absent stages get their identity values).
 enum { T_BIAS = 0, T_M1, T_R1, T_LO1, T_HI1, T_M2, T_R2, T_LO2, T_HI2, T_SCALE, T_SHIFT, T_COUNT };
-enum { EPI_N1 = 1, EPI_RES = 2, EPI_N2 = 4, EPI_AFF = 8 };
+enum { EPI_N1 = 1, EPI_RES = 2, EPI_N2 = 4, EPI_AFF = 8, EPI_STATS = 16 };
 
 __device__ __forceinline__ void fill_epilogue_table(float* s_tab, const EpiDev& e, int Cout, int Cout_pad, int nthreads) {
     for (int ch = threadIdx.x; ch < Cout_pad; ch += nthreads) {
@@ -213,6 +213,9 @@ __device__ __forceinline__ PixCtx make_pix(const OutDesc& o, const EpiDev& e, in
     return px;
 }
 
+// ALL: the NCHW and finished-frame outputs too (the FLAGS < 0 instantiations; the specialised ones only write planes / NHWC, and
+// keeping the frame code out of them keeps the full-chain kernel below the register ceiling).
+template <bool ALL>
 __device__ __forceinline__ void store_group(const OutDesc& p, const float* v, const PixCtx& px, int c0, int nvalid) {
     if (p.out_mode == RRV_OUT_PLANES) {
         uint4 hi, lo;
@@ -229,6 +232,8 @@ __device__ __forceinline__ void store_group(const OutDesc& p, const float* v, co
             for (int k = 0; k < 8; ++k)
                 if (k < nvalid) o[k] = v[k];
         }
+    } else if (!ALL) {
+        return;
     } else if (p.out_mode == RRV_OUT_F32_NCHW) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
@@ -347,6 +352,75 @@ __device__ __forceinline__ void chain8(const EpiDev& e, const float* s_tab, int 
 #endif
 }
 
+// ---- statistics fused into the epilogue (rrv_conv.stats) ------------------------------------------------------------------
+// A warp holds 32 pixels (lanes) x 32 channels (registers).  The butterfly below leaves lane L with the reduction over the 32
+// pixels of channel L in 31 shuffles: at distance d a lane keeps the half of its values its side of the exchange owns and
+// receives the partner's copy of that half.
+template <class Op>
+__device__ __forceinline__ float transpose_reduce32(const float* v, int lane, Op op) {
+    float a16[16], a8[8], a4[4], a2[2];
+    {
+        const bool up = (lane & 16) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a16[i] = op(up ? v[i + 16] : v[i], __shfl_xor_sync(0xffffffffu, up ? v[i] : v[i + 16], 16));
+    }
+    {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a8[i] = op(up ? a16[i + 8] : a16[i], __shfl_xor_sync(0xffffffffu, up ? a16[i] : a16[i + 8], 8));
+    }
+    {
+        const bool up = (lane & 4) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a4[i] = op(up ? a8[i + 4] : a8[i], __shfl_xor_sync(0xffffffffu, up ? a8[i] : a8[i + 4], 4));
+    }
+    {
+        const bool up = (lane & 2) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a2[i] = op(up ? a4[i + 2] : a4[i], __shfl_xor_sync(0xffffffffu, up ? a4[i] : a4[i + 2], 2));
+    }
+    const bool up = (lane & 1) != 0;
+    return op(up ? a2[1] : a2[0], __shfl_xor_sync(0xffffffffu, up ? a2[0] : a2[1], 1));
+}
+
+constexpr int STAT_SLOTS = 4;          // 32-channel chunks one epilogue warp can own: BN <= 256 over two warps per quadrant
+struct StatAcc {                       // per lane: channel (chunk base + lane) of each owned chunk
+    double s[STAT_SLOTS], q[STAT_SLOTS];
+    float mn[STAT_SLOTS], mx[STAT_SLOTS];
+};
+
+template <int SLOT>
+__device__ __forceinline__ void stat_add(StatAcc& a, const float* xs, bool valid, int lane, bool minmax) {
+    float t[CW];
+#pragma unroll
+    for (int i = 0; i < CW; ++i) t[i] = valid ? xs[i] : 0.0f;
+    a.s[SLOT] += (double)transpose_reduce32(t, lane, [](float x, float y) { return x + y; });
+    if (minmax) {
+#pragma unroll
+        for (int i = 0; i < CW; ++i) t[i] = valid ? xs[i] : CUDART_INF_F;
+        a.mn[SLOT] = fminf(a.mn[SLOT], transpose_reduce32(t, lane, [](float x, float y) { return fminf(x, y); }));
+#pragma unroll
+        for (int i = 0; i < CW; ++i) t[i] = valid ? xs[i] : -CUDART_INF_F;
+        a.mx[SLOT] = fmaxf(a.mx[SLOT], transpose_reduce32(t, lane, [](float x, float y) { return fmaxf(x, y); }));
+    }
+#pragma unroll
+    for (int i = 0; i < CW; ++i) t[i] = valid ? xs[i] * xs[i] : 0.0f;
+    a.q[SLOT] += (double)transpose_reduce32(t, lane, [](float x, float y) { return x + y; });
+}
+
+template <int SLOT>
+__device__ __forceinline__ void stat_flush(StatAcc& a, double* stats, int C, int ch, bool minmax) {
+    if (ch < C) {
+        atomicAdd(stats + C + ch, a.s[SLOT]);
+        atomicAdd(stats + 2 * C + ch, a.q[SLOT]);
+        if (minmax) {
+            atomic_min_double(stats + 3 * C + ch, (double)a.mn[SLOT]);
+            atomic_max_double(stats + 4 * C + ch, (double)a.mx[SLOT]);
+        }
+    }
+    a.s[SLOT] = 0.0; a.q[SLOT] = 0.0; a.mn[SLOT] = CUDART_INF_F; a.mx[SLOT] = -CUDART_INF_F;
+}
+
 // One CW-channel chunk of one accumulator row (= one output pixel): tcgen05.ld, the fused chain, the stores.
 // cb = first global output channel of the chunk, col0 = its first column inside the Cout tile.
 // FLAGS >= 0 fixes the set of stages at compile time (EPI_* bits); FLAGS < 0 reads it from `e`.
@@ -358,8 +432,10 @@ __device__ __forceinline__ void chain8(const EpiDev& e, const float* s_tab, int 
 template <int FLAGS, int MODE>
 __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e, const float* s_tab, int ts, uint32_t taddr,
                                                const PixCtx& px, int cb, int col0, int BN, bool pre = false,
-                                               const uint4* pre_rh = nullptr, const uint4* pre_rl = nullptr, int upx = 0) {
+                                               const uint4* pre_rh = nullptr, const uint4* pre_rl = nullptr, int upx = 0,
+                                               float* xs = nullptr) {
     constexpr bool DXM = MODE == 1;
+    constexpr bool STATS = FLAGS >= 0 && (FLAGS & EPI_STATS) != 0;       // xs receives the CW finished values (0 beyond Cout)
     const bool has_res = FLAGS >= 0 ? (FLAGS & EPI_RES) != 0 : e.res_hi != nullptr;
     // the residual of the whole chunk goes in flight first, ahead of the TMEM loads and the tap combine (volatile loads: the
     // compiler would otherwise sink them to their first use to save registers, and the chain then waits for L2)
@@ -445,7 +521,7 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
         }
     }
     if (MODE == 0) ptx::tmem_ld32_wait(r);
-    if (!px.valid) return;
+    if (!STATS && !px.valid) return;       // (with statistics every lane stays for the warp-wide reduction that follows)
     if (full && o.out_mode == RRV_OUT_PLANES) {
         // fast path (every per-frame layer but the RGB head): no per-group range checks, planes output
         uint16_t* oh = o.out_hi + px.out_off + cb;
@@ -454,6 +530,11 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
         for (int g = 0; g < CW / 8; ++g) {
             float x[8];
             chain8<FLAGS>(e, s_tab, ts, cb + g * 8, r + g * 8, x, rh[g], rl[g], true, px, o.Cout);
+            if (STATS) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) xs[g * 8 + k] = x[k];
+                if (!px.valid) continue;
+            }
             uint4 hi, lo;
             split8(x, hi, lo);
             *reinterpret_cast<uint4*>(oh + g * 8) = hi;
@@ -464,10 +545,21 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
 #pragma unroll
     for (int g = 0; g < CW / 8; ++g) {
         const int c0 = cb + g * 8;
-        if (c0 >= o.Cout || col0 + g * 8 >= BN) continue;
+        if (c0 >= o.Cout || col0 + g * 8 >= BN) {
+            if (STATS) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) xs[g * 8 + k] = 0.0f;
+            }
+            continue;
+        }
         float x[8];
         chain8<FLAGS>(e, s_tab, ts, c0, r + g * 8, x, rh[g], rl[g], full, px, o.Cout);
-        store_group(o, x, px, c0, c0 + 8 <= o.Cout ? 8 : o.Cout - c0);
+        if (STATS) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) xs[g * 8 + k] = x[k];
+            if (!px.valid) continue;
+        }
+        store_group<(FLAGS < 0)>(o, x, px, c0, c0 + 8 <= o.Cout ? 8 : o.Cout - c0);
     }
 }
 
@@ -738,6 +830,8 @@ struct Tc2Params {
     int a_stages, b_slots, b_resident, pair;
     int a_plane_bytes;      // (16 MT + 2) * 1024 (16 MT for 1x1)
     int acc_stride, set_stride, bufs, tmem_cols;
+    double* stats;          // rrv_conv.stats: double[5][Cout] accumulated by the epilogue (EPI_STATS instantiations), or NULL
+    int stats_minmax;
     EpiDev ep;
 };
 
@@ -1086,6 +1180,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int ty = DXM ? quad : (m >> 3), tx = DXM ? lane : (m & 7);
         const int nchunks = (p.BNe + CW - 1) / CW;
         const EpiDev& e = p.ep;
+        constexpr bool STATS = FLAGS >= 0 && (FLAGS & EPI_STATS) != 0;
+        StatAcc sacc;
+        if (STATS) {
+#pragma unroll
+            for (int j = 0; j < STAT_SLOTS; ++j) { sacc.s[j] = 0.0; sacc.q[j] = 0.0; sacc.mn[j] = CUDART_INF_F; sacc.mx[j] = -CUDART_INF_F; }
+        }
+        const bool st_mm = STATS && p.stats_minmax != 0;
+        int st_n0 = 0;
         int as = 0;
         uint32_t aphase = 0;
         for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
@@ -1170,9 +1272,30 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const int oy = p.nph == 4 ? 2 * iy + (ph >> 1) : iy;
                 const int ox = p.nph == 4 ? 2 * ix + (ph & 1) : ix;
                 const PixCtx px = make_pix(p.o, e, n, oy, ox, valid);
+                if (STATS) {
+                    // the finished values of each chunk also go into this warp's per-channel accumulators (slot j = its j-th chunk)
+#define RRV_STAT_CHUNK(J)                                                                                                              \
+    if (half + 2 * (J) < nchunks) {                                                                                                    \
+        const int ch = half + 2 * (J);                                                                                                 \
+        float xs[CW];                                                                                                                  \
+        epilogue_chunk<FLAGS, DXM ? 1 : 0>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, ch * CW, p.BNe, false, \
+                                           nullptr, nullptr, 0, xs);                                                                   \
+        stat_add<(J)>(sacc, xs, valid, lane, st_mm);                                                                                   \
+    }
+                    RRV_STAT_CHUNK(0) RRV_STAT_CHUNK(1) RRV_STAT_CHUNK(2) RRV_STAT_CHUNK(3)
+#undef RRV_STAT_CHUNK
+                    st_n0 = n0;
+                    continue;
+                }
                 for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4)
                     epilogue_chunk<FLAGS, DXM ? 1 : 0>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, ch * CW, p.BNe,
                                                pre && mt == 0 && ch == half, pre_rh, pre_rl);
+            }
+            if (STATS && p.n_ntiles > 1) {           // the next tile may cover other channels: flush (one atomic per channel and quantity)
+                stat_flush<0>(sacc, p.stats, p.Cout, st_n0 + (half + 0) * CW + lane, st_mm);
+                stat_flush<1>(sacc, p.stats, p.Cout, st_n0 + (half + 2) * CW + lane, st_mm);
+                stat_flush<2>(sacc, p.stats, p.Cout, st_n0 + (half + 4) * CW + lane, st_mm);
+                stat_flush<3>(sacc, p.stats, p.Cout, st_n0 + (half + 6) * CW + lane, st_mm);
             }
             ptx::tc_fence_before();
             __syncwarp();
@@ -1181,6 +1304,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 else ptx::mbar_arrive(ptx::smem_u32(&s_tempty[as]));
             }
             if (++as == p.bufs) { as = 0; aphase ^= 1u; }
+        }
+        if (STATS && p.n_ntiles == 1) {              // one Cout tile: the lane-to-channel map never changed, one flush per kernel
+            stat_flush<0>(sacc, p.stats, p.Cout, (half + 0) * CW + lane, st_mm);
+            stat_flush<1>(sacc, p.stats, p.Cout, (half + 2) * CW + lane, st_mm);
+            stat_flush<2>(sacc, p.stats, p.Cout, (half + 4) * CW + lane, st_mm);
+            stat_flush<3>(sacc, p.stats, p.Cout, (half + 6) * CW + lane, st_mm);
         }
     }
 
@@ -1395,7 +1524,8 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     int a_stage = 0, b_slot = 0, box_w = 8, box_rows = 0;
     d.dxm = (g_tune.dxm && p->ksize == 3 && !ups && 3 * d.Cout_pad <= 256 && d.in_W >= 16) ? 1 : 0;
     static const bool no_ups_merge = getenv("RRV_NO_UPS_MERGE") != nullptr;      // A/B switch for measurements
-    if (!no_ups_merge && g_tune.dxm && p->ksize == 3 && ups && 4 * d.Cout_pad <= 256 && d.Cout_pad % CW == 0 && d.in_W >= 16 && p->out_mode == RRV_OUT_PLANES)
+    if (!no_ups_merge && g_tune.dxm && p->ksize == 3 && ups && 4 * d.Cout_pad <= 256 && d.Cout_pad % CW == 0 && d.in_W >= 16 &&
+        p->out_mode == RRV_OUT_PLANES && p->stats == nullptr)
         d.dxm = 2;
     const int xchg_bytes = (p->pool && d.dxm) ? EPI_WARPS * 512 : 0;       // row-partner exchange of the fused max-pool
     const int budget = SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES - xchg_bytes;
@@ -1572,6 +1702,8 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     d.total_tiles = (int)total;
     d.ep = make_epi(p->ep, p->Cout);
     d.ep.lo_fp16 = 0;
+    d.stats = p->stats;
+    d.stats_minmax = p->stats_minmax;
 
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     const int rows = btiles * d.Cout_pad;
@@ -1588,11 +1720,20 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         mb_lo = mb_hi;
     }
     const int smem = d.a_stages * a_stage + d.b_slots * b_slot + d.Cout_pad * TAB_BYTES + xchg_bytes + 1024;
-    const int flags = epi_flags(p->ep);
+    // the specialised instantiations write planes / NHWC only; NCHW and the finished BGR frame (the RGB head) take the generic one
+    const bool plain_out = p->out_mode == RRV_OUT_PLANES || p->out_mode == RRV_OUT_F32_NHWC;
+    const int flags = plain_out ? epi_flags(p->ep) : -1;
     const int grid = d.pair ? 2 * std::min(d.total_tiles, num_sms() / 2) : std::min(d.total_tiles, num_sms());
+    if (p->stats != nullptr) {          // statistics of the written values from the epilogue (bias + activation only)
+        if (d.dxm) {
+            if (d.pair) return launch_tc2p<EPI_STATS, true, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+            return launch_tc2p<EPI_STATS, false, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        }
+        return launch_tc2<EPI_STATS>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+    }
     if (d.dxm) {
         // merged-tap layers: conv1_2 (bias + ReLU [+ pool]), slice2.conv2 (the full chain), the RGB head / anything else (generic)
-        const int f = (flags == 0 || flags == (EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF)) ? flags : -1;
+        const int f = (flags == 0 || flags == (EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF)) ? flags : -1;      // (flags < 0 stays generic)
         if (flags == EPI_N1) {          // slice2.conv1 (merged column phases)
             if (d.pair) return launch_tc2p<EPI_N1, true, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
             return launch_tc2p<EPI_N1, false, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
@@ -1698,6 +1839,11 @@ int conv2d_tc(const rrv_conv* p, cudaStream_t st) {
         RRV_REQUIRE(p->out_mode != RRV_OUT_F32_NCHW || p->out_C > 0, "rrv_conv2d: out_C must be set for NCHW output");
     }
     RRV_REQUIRE(p->terms >= RRV_TERMS_FULL && p->terms <= RRV_TERMS_NO_ALO, "rrv_conv2d: bad terms %d", p->terms);
+    if (p->stats != nullptr) {
+        RRV_REQUIRE(g_tune.version == 2 && !(ups && g_tune.ups_v1), "rrv_conv2d(stats): needs the v2 main loop");
+        RRV_REQUIRE(!p->pool && epi_flags(p->ep) == 0, "rrv_conv2d(stats): only bias + activation may precede the fused statistics");
+        RRV_REQUIRE(p->out_mode == RRV_OUT_PLANES || p->out_mode == RRV_OUT_F32_NHWC, "rrv_conv2d(stats): planes or NHWC output");
+    }
 
     if (p->pool) {
         RRV_REQUIRE(!ups && p->out_mode == RRV_OUT_PLANES && p->Cout % 32 == 0 && g_tune.version == 2,
@@ -1756,7 +1902,8 @@ int conv2d_tc(const rrv_conv* p, cudaStream_t st) {
 
     const int smem = d.stages * stage_bytes + tab_bytes + 1024;
     const int grid = std::min(d.total_tiles, num_sms());
-    switch (epi_flags(p->ep)) {
+    const bool plain_out = p->out_mode == RRV_OUT_PLANES || p->out_mode == RRV_OUT_F32_NHWC;
+    switch (plain_out ? epi_flags(p->ep) : -1) {
         case 0: return launch_tc1<0>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
         case EPI_N1: return launch_tc1<EPI_N1>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
         default: return launch_tc1<-1>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);

@@ -1,6 +1,8 @@
 // HBM-bound pointwise kernels: 2x2 max-pool on planes, the epilogue chain alone (pre-pass
 // normalisation), layout conversions, the de-normalise/clamp/BGR postprocess and the fp32
 // weight repack.  All vectorised to 16-byte accesses along the channel dimension.
+#include <math_constants.h>
+
 #include "rrv_common.cuh"
 
 namespace rrv {
@@ -57,11 +59,20 @@ int maxpool2x2(const void* in_hi, const void* in_lo, int N, int H, int W, int C,
 }
 
 // ---- epilogue chain alone over fp32 NHWC ----
+// STATS: the per-channel {sum, sum of squares[, min, max]} of the values written also go to `stats` (double[5][C]).  A thread keeps
+// one 8-channel group for the whole kernel (the grid stride is a multiple of C / 8), sums its pixels in fp32 (a few dozen values),
+// the block combines the threads of equal group in double through shared memory and issues one atomic per channel and quantity.
+template <bool STATS>
 __global__ void __launch_bounds__(256) pointwise_kernel(const float* __restrict__ in, long long in_bs, int N, int H, int W,
                                                         int C, EpiDev ep, int out_mode, uint16_t* out_hi,
-                                                        uint16_t* out_lo, float* out_f32) {
+                                                        uint16_t* out_lo, float* out_f32, double* stats, int stats_minmax) {
     const int C8 = C >> 3;
     const long long total = (long long)N * H * W * C8;
+    float ssum[8], ssq[8], smn[8], smx[8];
+    if (STATS) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ssum[k] = 0.0f; ssq[k] = 0.0f; smn[k] = CUDART_INF_F; smx[k] = -CUDART_INF_F; }
+    }
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
         const int c0 = (int)(i % C8) * 8;
         long long t = i / C8;
@@ -73,6 +84,15 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const float* __restrict_
         const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
         v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
         apply_epilogue<8>(ep, v, n, y, x, c0);
+        if (STATS) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                ssum[k] += v[k];
+                ssq[k] = fmaf(v[k], v[k], ssq[k]);
+                smn[k] = fminf(smn[k], v[k]);
+                smx[k] = fmaxf(smx[k], v[k]);
+            }
+        }
         const long long o = (((long long)n * H + y) * W + x) * C + c0;
         if (out_mode == RRV_OUT_PLANES) {
             store8(out_hi + o, out_lo ? out_lo + o : nullptr, ep.lo_fp16, v);
@@ -81,10 +101,38 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const float* __restrict_
             *reinterpret_cast<float4*>(out_f32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
     }
+    if (STATS) {
+        // threads t, t + C8, t + 2 C8, ... of the block own the same channel group (256 % C8 == 0)
+        __shared__ float s_red[4][256][8 + 1];
+        const int t = threadIdx.x;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s_red[0][t][k] = ssum[k]; s_red[1][t][k] = ssq[k]; s_red[2][t][k] = smn[k]; s_red[3][t][k] = smx[k]; }
+        __syncthreads();
+        const int groups = C8 < 256 ? C8 : 256;
+        for (int j = t; j < groups * 8; j += 256) {
+            const int g = j >> 3, k = j & 7;
+            double a = 0.0, b = 0.0;
+            float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+            for (int u = g; u < 256; u += groups) {
+                a += (double)s_red[0][u][k];
+                b += (double)s_red[1][u][k];
+                mn = fminf(mn, s_red[2][u][k]);
+                mx = fmaxf(mx, s_red[3][u][k]);
+            }
+            // which channel group does thread g own?  i = blockIdx.x * 256 + g (+ multiples of the stride): c0 = (i % C8) * 8
+            const int c = (int)(((long long)blockIdx.x * 256 + g) % C8) * 8 + k;
+            atomicAdd(stats + C + c, a);
+            atomicAdd(stats + 2 * C + c, b);
+            if (stats_minmax) {
+                atomic_min_double(stats + 3 * C + c, (double)mn);
+                atomic_max_double(stats + 4 * C + c, (double)mx);
+            }
+        }
+    }
 }
 
 int pointwise(const float* in, long long in_bs, int N, int H, int W, int C, const rrv_epilogue* ep, int out_mode,
-              void* out_hi, void* out_lo, float* out_f32, cudaStream_t st) {
+              void* out_hi, void* out_lo, float* out_f32, double* stats, int stats_minmax, cudaStream_t st) {
     RRV_REQUIRE(in && ep, "rrv_pointwise: NULL input");
     RRV_REQUIRE(C % 8 == 0, "rrv_pointwise: C must be a multiple of 8 (got %d)", C);
     RRV_REQUIRE(out_mode == RRV_OUT_PLANES || out_mode == RRV_OUT_F32_NHWC, "rrv_pointwise: bad out_mode %d", out_mode);
@@ -92,8 +140,14 @@ int pointwise(const float* in, long long in_bs, int N, int H, int W, int C, cons
     const long long total = (long long)N * H * W * (C / 8);
     if (total == 0) return 0;
     const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
-    pointwise_kernel<<<grid, 256, 0, st>>>(in, in_bs, N, H, W, C, make_epi(*ep, C), out_mode, (uint16_t*)out_hi,
-                                           (uint16_t*)out_lo, out_f32);
+    if (stats != nullptr) {
+        RRV_REQUIRE(C <= 2048 && 256 % (C / 8 < 256 ? C / 8 : 256) == 0 && (C / 8 <= 256), "rrv_pointwise_stats: C / 8 must divide 256 (C=%d)", C);
+        pointwise_kernel<true><<<grid, 256, 0, st>>>(in, in_bs, N, H, W, C, make_epi(*ep, C), out_mode, (uint16_t*)out_hi,
+                                                     (uint16_t*)out_lo, out_f32, stats, stats_minmax);
+        return check_launch("pointwise_kernel<stats>");
+    }
+    pointwise_kernel<false><<<grid, 256, 0, st>>>(in, in_bs, N, H, W, C, make_epi(*ep, C), out_mode, (uint16_t*)out_hi,
+                                                  (uint16_t*)out_lo, out_f32, nullptr, 0);
     return check_launch("pointwise_kernel");
 }
 
@@ -249,6 +303,67 @@ int pack_weights_f32(const float* w, int Cin, int Cout, int ksize, int Cin_pad, 
     const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 8);
     pack_w_f32_kernel<<<grid, 256, 0, st>>>(w, Cin, Cout, ksize * ksize, Cin_pad, Cout_pad, out);
     return check_launch("pack_w_f32_kernel");
+}
+
+}  // namespace rrv
+
+// ---- KernelFilter fold (engine.StyleEngine._fold_filter on the device) -----------------------------------------------
+// The two predicted 32x32 matrices of a KernelFilter (apply_filter, style_network_global.py:194-217) are absorbed by the
+// neighbouring convolutions:  Wf1 . conv_down(x) = conv_{Wf1 . Wdown}(x),  conv_up(Wf2 . t) = conv_{Wup . Wf2}(t).
+// This kernel computes both products in fp32 and writes them straight into the tensor-core weight blobs
+// ([tap][Cout_pad][Cin] bf16 hi, then lo; the 32 inner channels zero-padded to 64), plus the folded down bias:
+// frame mode predicts new filters for every frame, so the fold must not cost library GEMMs, allocations and repack launches.
+namespace rrv {
+
+constexpr int KF_IN = 32, KF_PAD = 64, KF_C = 512;
+
+__global__ void __launch_bounds__(256) fold_filter_kernel(const float* __restrict__ wf1, const float* __restrict__ wf2,
+                                                          const float* __restrict__ down_w, const float* __restrict__ down_b,
+                                                          const float* __restrict__ up_w, uint16_t* __restrict__ down_blob,
+                                                          float* __restrict__ down_bias, uint16_t* __restrict__ up_blob) {
+    __shared__ float s_f1[KF_IN * KF_IN], s_f2[KF_IN * KF_IN];
+    for (int i = threadIdx.x; i < KF_IN * KF_IN; i += 256) { s_f1[i] = wf1[i]; s_f2[i] = wf2[i]; }
+    __syncthreads();
+    const long long n_down = 9LL * KF_PAD * KF_C, n_up = 9LL * KF_C * KF_PAD;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_down + n_up + KF_PAD; i += (long long)gridDim.x * 256) {
+        if (i < n_down) {                       // down blob: [t][co (64)][ci (512)]
+            const int ci = (int)(i % KF_C), co = (int)((i / KF_C) % KF_PAD), t = (int)(i / ((long long)KF_C * KF_PAD));
+            float v = 0.0f;
+            if (co < KF_IN) {
+#pragma unroll 8
+                for (int j = 0; j < KF_IN; ++j) v = fmaf(s_f1[co * KF_IN + j], __ldg(down_w + ((long long)j * KF_C + ci) * 9 + t), v);
+            }
+            uint16_t h, l;
+            split_hi_lo(v, 0, h, l);
+            down_blob[i] = h;
+            down_blob[n_down + i] = l;
+        } else if (i < n_down + n_up) {         // up blob: [t][o (512)][ci (64)]
+            const long long k = i - n_down;
+            const int ci = (int)(k % KF_PAD), o = (int)((k / KF_PAD) % KF_C), t = (int)(k / ((long long)KF_PAD * KF_C));
+            float v = 0.0f;
+            if (ci < KF_IN) {
+#pragma unroll 8
+                for (int j = 0; j < KF_IN; ++j) v = fmaf(__ldg(up_w + ((long long)o * KF_IN + j) * 9 + t), s_f2[j * KF_IN + ci], v);
+            }
+            uint16_t h, l;
+            split_hi_lo(v, 0, h, l);
+            up_blob[k] = h;
+            up_blob[n_up + k] = l;
+        } else {                                // folded down bias, padded to 64
+            const int co = (int)(i - n_down - n_up);
+            float v = 0.0f;
+            if (co < KF_IN)
+                for (int j = 0; j < KF_IN; ++j) v = fmaf(s_f1[co * KF_IN + j], __ldg(down_b + j), v);
+            down_bias[co] = v;
+        }
+    }
+}
+
+int fold_filter(const float* wf1, const float* wf2, const float* down_w, const float* down_b, const float* up_w, void* down_blob,
+                float* down_bias, void* up_blob, cudaStream_t st) {
+    RRV_REQUIRE(wf1 && wf2 && down_w && down_b && up_w && down_blob && down_bias && up_blob, "rrv_fold_filter: NULL tensor");
+    fold_filter_kernel<<<148 * 4, 256, 0, st>>>(wf1, wf2, down_w, down_b, up_w, (uint16_t*)down_blob, down_bias, (uint16_t*)up_blob);
+    return check_launch("fold_filter_kernel");
 }
 
 }  // namespace rrv

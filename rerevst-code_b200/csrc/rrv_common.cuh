@@ -180,4 +180,24 @@ __device__ __forceinline__ void apply_epilogue(const EpiDev& e, float* v, int n,
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// ---- double min / max atomics (statistics partials) ----
+__device__ __forceinline__ void atomic_min_double(double* a, double v) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(a);
+    unsigned long long old = *p;
+    while (__longlong_as_double((long long)old) > v) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+__device__ __forceinline__ void atomic_max_double(double* a, double v) {
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(a);
+    unsigned long long old = *p;
+    while (__longlong_as_double((long long)old) < v) {
+        const unsigned long long assumed = old;
+        old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
+        if (old == assumed) break;
+    }
+}
+
 }  // namespace rrv

@@ -4,8 +4,8 @@
 // of the normalised tensor over batch and space in two passes; EncoderStyle.cal_mean_std
 // (:304-315) takes mean and unbiased std; FilterPredictor.compute (:161-172) takes a spatial
 // and batch mean followed by a 64 -> 1024 linear layer.  Here one two-pass reduction produces
-// mergeable partials {count, sum, M2, min, max} in double precision (warp shuffles inside a
-// warp, shared memory across warps, one atomic per channel per block), so that ranks of the
+// mergeable partials {count, sum, M2, min, max} in double precision (per-thread accumulation over a
+// strip of pixels, shared memory across the threads of a block, one atomic per channel per block), so that ranks of the
 // frame-parallel driver can all-gather and merge them (Chan et al.) in a fixed order.
 #include <math_constants.h>
 
@@ -14,25 +14,6 @@
 namespace rrv {
 
 constexpr int ST_PIX = 2048;   // pixels per block
-
-__device__ __forceinline__ void atomic_min_double(double* a, double v) {
-    unsigned long long* p = reinterpret_cast<unsigned long long*>(a);
-    unsigned long long old = *p;
-    while (__longlong_as_double((long long)old) > v) {
-        const unsigned long long assumed = old;
-        old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
-        if (old == assumed) break;
-    }
-}
-__device__ __forceinline__ void atomic_max_double(double* a, double v) {
-    unsigned long long* p = reinterpret_cast<unsigned long long*>(a);
-    unsigned long long old = *p;
-    while (__longlong_as_double((long long)old) < v) {
-        const unsigned long long assumed = old;
-        old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
-        if (old == assumed) break;
-    }
-}
 
 __global__ void stats_init_kernel(double* part, int C, double count) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -102,6 +83,29 @@ int channel_stats(const float* x, long long npix, int C, double* part, cudaStrea
     if (check_launch("stats_kernel<0>")) return 1;
     stats_kernel<1><<<grid, 256, 0, st>>>(x, npix, C, part);
     return check_launch("stats_kernel<1>");
+}
+
+int stats_init(double* part, int C, double count, cudaStream_t st) {
+    RRV_REQUIRE(part && C > 0, "rrv_stats_init: bad arguments");
+    stats_init_kernel<<<ceil_div(C, 256), 256, 0, st>>>(part, C, count);
+    return check_launch("stats_init_kernel");
+}
+
+// Partials accumulated in ONE pass by a producing kernel (rrv_conv.stats, rrv_pointwise's stats) hold sum(x^2) in row 2;
+// M2 about the mean = sum(x^2) - sum(x)^2 / n, in double (the inputs are fp32 values: ~2^-29 relative on M2 for data whose
+// mean and spread are comparable, as every tensor on this path is).
+__global__ void stats_sums_to_m2_kernel(double* part, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double n = part[c], s = part[C + c], q = part[2 * C + c];
+    const double m2 = q - s * s / n;
+    part[2 * C + c] = m2 > 0.0 ? m2 : 0.0;
+}
+
+int stats_sums_to_m2(double* part, int C, cudaStream_t st) {
+    RRV_REQUIRE(part && C > 0, "rrv_stats_sums_to_m2: bad arguments");
+    stats_sums_to_m2_kernel<<<ceil_div(C, 128), 128, 0, st>>>(part, C);
+    return check_launch("stats_sums_to_m2_kernel");
 }
 
 // Chan/Golub/LeVeque pairwise merge, applied left to right over the parts (deterministic).

@@ -80,6 +80,31 @@ class ConvW:
         self._keep = w
 
 
+class FoldedFilter:
+    """The two convolutions of one KernelFilter with its predicted 32x32 matrices folded in, as preallocated tensor-core
+    weight blobs that rrv_fold_filter rewrites in place (frame mode: new filters every frame, no allocation, no library GEMM)."""
+
+    class _W:
+        __slots__ = ("Cin", "Cout", "ksize", "ups", "Cin_used", "bias", "w_f32", "w_tc")
+
+    def __init__(self, fw, device):
+        lib = L.lib()
+        self.down, self.up = FoldedFilter._W(), FoldedFilter._W()
+        for w, cin, cout, used in ((self.down, 512, INNER_PAD, 0), (self.up, INNER_PAD, 512, 32)):
+            w.Cin, w.Cout, w.ksize, w.ups, w.Cin_used, w.w_f32 = cin, cout, 3, False, used, None
+            w.w_tc = torch.empty(lib.rrv_tc_weight_bytes(cin, cout, 3, 0), dtype=torch.uint8, device=device)
+        self.down.bias = torch.zeros(INNER_PAD, dtype=torch.float32, device=device)
+        self.up.bias = fw["up_b"]
+        self._src = (fw["down_w"].contiguous(), fw["down_b"].contiguous(), fw["up_w"].contiguous())
+
+    def fold(self, wf1, wf2):
+        dw, db, uw = self._src
+        L.check(L.lib().rrv_fold_filter(wf1.data_ptr(), wf2.data_ptr(), dw.data_ptr(), db.data_ptr(), uw.data_ptr(),
+                                        self.down.w_tc.data_ptr(), self.down.bias.data_ptr(), self.up.w_tc.data_ptr(), L.stream()),
+                "rrv_fold_filter")
+        return self.down, self.up
+
+
 def make_epilogue(bias=None, act=0, norm1=None, res=None, res_shift=0, res_broadcast=False, norm2=None, affine=None):
     e = L.Epilogue()
     e.bias = L.ptr(bias)
@@ -176,7 +201,8 @@ class StyleEngine:
                 self._fold_filter(f, a, b)
 
     # ------------------------------------------------------------------ thin wrappers over the C ABI
-    def _conv(self, cw, x, ep, out_mode=L.OUT_PLANES, out=None, N=None, out_C=0, pool=False, crop=None, terms=0):
+    def _conv(self, cw, x, ep, out_mode=L.OUT_PLANES, out=None, N=None, out_C=0, pool=False, crop=None, terms=0, stats=None,
+              stats_minmax=False):
         N = x.N if N is None else N
         H, W = (x.H * 2, x.W * 2) if cw.ups else (x.H, x.W)
         if pool and (self._impl_for(cw) != L.IMPL_TCGEN05 or cw.Cout % 32 != 0 or H < 2 or W < 2):
@@ -191,6 +217,8 @@ class StyleEngine:
         d.pool = int(pool)
         d.Cin_used = cw.Cin_used
         d.terms = terms
+        if stats is not None:
+            d.stats, d.stats_minmax = stats.data_ptr(), int(stats_minmax)
         if out_mode in (L.OUT_BGR_F32, L.OUT_BGR_U8):      # the RGB head writes the post-processed, cropped HWC BGR frame
             y0, x0, h, w = crop if crop is not None else (0, 0, H, W)
             dt = torch.float32 if out_mode == L.OUT_BGR_F32 else torch.uint8
@@ -242,19 +270,68 @@ class StyleEngine:
         then three nearest x2 upsamples -- (H // 8) * 8, e.g. 436 x 1024 -> 432 x 1024, like the reference."""
         return (H // 8) * 8, (W // 8) * 8
 
-    def _pointwise(self, x_f32, ep, N=None, broadcast=False, to_f32=False):
+    def _pointwise(self, x_f32, ep, N=None, broadcast=False, to_f32=False, stats=None, stats_minmax=False):
         n_in, H, W, Cc = x_f32.shape
         N = n_in if N is None else N
         bs = 0 if broadcast else H * W * Cc
         if to_f32:
             out = torch.empty((N, H, W, Cc), dtype=torch.float32, device=self.device)
-            L.check(self.lib.rrv_pointwise(x_f32.data_ptr(), bs, N, H, W, Cc, C.byref(ep), L.OUT_F32_NHWC, 0, 0,
-                                           out.data_ptr(), L.stream()), "rrv_pointwise")
+            args = (x_f32.data_ptr(), bs, N, H, W, Cc, C.byref(ep), L.OUT_F32_NHWC, 0, 0, out.data_ptr())
         else:
             out = Planes(N, H, W, Cc, self.x3, self.device)
-            L.check(self.lib.rrv_pointwise(x_f32.data_ptr(), bs, N, H, W, Cc, C.byref(ep), L.OUT_PLANES, L.ptr(out.hi),
-                                           L.ptr(out.lo), 0, L.stream()), "rrv_pointwise")
+            args = (x_f32.data_ptr(), bs, N, H, W, Cc, C.byref(ep), L.OUT_PLANES, L.ptr(out.hi), L.ptr(out.lo), 0)
+        if stats is not None:
+            L.check(self.lib.rrv_pointwise_stats(*args, stats.data_ptr(), int(stats_minmax), L.stream()), "rrv_pointwise_stats")
+        else:
+            L.check(self.lib.rrv_pointwise(*args, L.stream()), "rrv_pointwise")
         return out
+
+    # ---- one-pass statistics: the kernel that writes a tensor also accumulates its per-channel sums (rrv_conv.stats) ----
+    @property
+    def fused_stats(self):
+        return self.impl_name != "ffma"
+
+    def _part_new(self, Cc, npix):
+        part = torch.empty((5, Cc), dtype=torch.float64, device=self.device)
+        L.check(self.lib.rrv_stats_init(part.data_ptr(), Cc, float(npix), L.stream()), "rrv_stats_init")
+        return part
+
+    def _part_done(self, part):
+        """{n, sum, sum of squares, min, max} -> {n, sum, M2, min, max}, merged over the ranks of a sharded pre-pass."""
+        Cc = part.shape[1]
+        L.check(self.lib.rrv_stats_sums_to_m2(part.data_ptr(), Cc, L.stream()), "rrv_stats_sums_to_m2")
+        return self._merge_ranks(part)
+
+    def _merge_ranks(self, part):
+        if self.stats_allgather is None:
+            return part
+        Cc = part.shape[1]
+        parts = self.stats_allgather(part).contiguous()              # frame-parallel pre-pass (dist.py)
+        merged = torch.empty_like(part)
+        L.check(self.lib.rrv_stats_merge(parts.data_ptr(), parts.shape[0], Cc, merged.data_ptr(), L.stream()), "rrv_stats_merge")
+        return merged
+
+    def _conv_stats(self, cw, x, ep, minmax, N=None):
+        """fp32 NHWC convolution output + the finished partial statistics of that output (one pass on the tensor-core path)."""
+        if not self.fused_stats or self._impl_for(cw) != L.IMPL_TCGEN05:
+            out = self._conv(cw, x, ep, L.OUT_F32_NHWC, N=N)
+            return out, self._stats_part(out)
+        n = x.N if N is None else N
+        H, W = (x.H * 2, x.W * 2) if cw.ups else (x.H, x.W)
+        part = self._part_new(cw.Cout, n * H * W)
+        out = self._conv(cw, x, ep, L.OUT_F32_NHWC, N=N, stats=part, stats_minmax=minmax)
+        return out, self._part_done(part)
+
+    def _pointwise_stats(self, x_f32, ep, minmax, **kw):
+        """pointwise pass + the finished partial statistics of what it wrote."""
+        n_in, H, W, Cc = x_f32.shape
+        n = kw.get("N") or n_in
+        if not self.fused_stats or 256 % (Cc // 8) != 0:
+            out = self._pointwise(x_f32, ep, to_f32=True, **kw)
+            return out, self._stats_part(out)
+        part = self._part_new(Cc, n * H * W)
+        out = self._pointwise(x_f32, ep, to_f32=True, stats=part, stats_minmax=minmax, **kw)
+        return out, self._part_done(part)
 
     def _pool(self, x):
         out = Planes(x.N, x.H // 2, x.W // 2, x.C, self.x3, self.device)
@@ -267,13 +344,7 @@ class StyleEngine:
         part = torch.empty((5, Cc), dtype=torch.float64, device=self.device)
         L.check(self.lib.rrv_channel_stats(x_f32.data_ptr(), x_f32.numel() // Cc, Cc, part.data_ptr(), L.stream()),
                 "rrv_channel_stats")
-        if self.stats_allgather is not None:                      # frame-parallel pre-pass (dist.py)
-            parts = self.stats_allgather(part).contiguous()
-            merged = torch.empty_like(part)
-            L.check(self.lib.rrv_stats_merge(parts.data_ptr(), parts.shape[0], Cc, merged.data_ptr(), L.stream()),
-                    "rrv_stats_merge")
-            part = merged
-        return part
+        return self._merge_ranks(part)
 
     def _finalize(self, part, kind, eps):
         Cc = part.shape[1]
@@ -309,6 +380,8 @@ class StyleEngine:
                     x = self._pointwise(taps[idx], ident)
             elif last and mode == "raw":
                 return self._conv(cw, x, ep, L.OUT_F32_NHWC)
+            elif last and mode == "raw+stats":
+                return self._conv_stats(cw, x, ep, False)
             elif last:
                 return self._conv(cw, x, make_epilogue(bias=cw.bias, act=1, norm1=norm0))
             else:
@@ -379,10 +452,16 @@ class StyleEngine:
         down_sample / upsample convolutions: Wf1 . conv_down(x) == conv_{Wf1.Wdown}(x) and
         conv_up(Wf2 . t) == conv_{Wup.Wf2}(t).  One-off per clip, fp32."""
         fw = self.w[f]
-        dw = torch.matmul(wf1, fw["down_w"].reshape(32, -1)).reshape(32, 512, 3, 3)
-        db = torch.mv(wf1, fw["down_b"])
-        uw = torch.einsum("ojyx,ji->oiyx", fw["up_w"], wf2).contiguous()
-        self.fw[f] = (ConvW(dw, db, cout_pad=INNER_PAD), ConvW(uw, fw["up_b"], cin_pad=INNER_PAD))
+        if self.impl_name != "ffma":                      # on the device, straight into tensor-core blobs (rrv_fold_filter)
+            ff = FoldedFilter(fw, self.device)
+            self.fw[f] = ff.fold(wf1.contiguous(), wf2.contiguous())
+            self._fold_keep = getattr(self, "_fold_keep", {})
+            self._fold_keep[f] = ff
+        else:                                             # FFMA bring-up path: fp32 weight layout through the generic repack
+            dw = torch.matmul(wf1, fw["down_w"].reshape(32, -1)).reshape(32, 512, 3, 3)
+            db = torch.mv(wf1, fw["down_b"])
+            uw = torch.einsum("ojyx,ji->oiyx", fw["up_w"], wf2).contiguous()
+            self.fw[f] = (ConvW(dw, db, cout_pad=INNER_PAD), ConvW(uw, fw["up_b"], cin_pad=INNER_PAD))
         self.filters[f] = (wf1, wf2)
 
     def _predict_filters(self, f, content):
@@ -390,7 +469,7 @@ class StyleEngine:
         run as one 512 -> 64 convolution; spatial+batch mean; Linear(64 -> 1024) each."""
         fw = self.w[f]
         ep = make_epilogue(bias=fw["pred"].bias)
-        c_mean = self._finalize(self._stats_part(self._conv(fw["pred"], content, ep, L.OUT_F32_NHWC)), 2, 0.0)[0]
+        c_mean = self._finalize(self._conv_stats(fw["pred"], content, ep, False)[1], 2, 0.0)[0]
         s = self._conv(fw["pred"], self.style["nstyle"], ep, L.OUT_F32_NHWC)
         part = torch.empty((5, 64), dtype=torch.float64, device=self.device)
         L.check(self.lib.rrv_channel_stats(s.data_ptr(), s.numel() // 64, 64, part.data_ptr(), L.stream()), "stats")
@@ -433,24 +512,25 @@ class StyleEngine:
             if i < 2:
                 h = self._pointwise(u0, make_epilogue(res=h), N=N, broadcast=True)
             else:
-                r = self._pointwise(u0, make_epilogue(res=h), N=N, broadcast=True, to_f32=True)
+                r, rpart = self._pointwise_stats(u0, make_epilogue(res=h), True, N=N, broadcast=True)
         levels = (("norm1", "relu4_1", "slice4"), ("norm2", "relu3_1", "slice3"),
                   ("norm3", "relu2_1", "slice2"), ("norm4", "relu1_1", None))
+        # every statistic comes out of the kernel that writes the tensor (rrv_conv.stats / rrv_pointwise_stats): no extra passes
         for nname, lvl, block in levels:
-            st[nname] = self._saved_stat(r)
+            st[nname] = self._finalize(rpart, 0, 1e-8)
             if block is None:
                 break
             h = self._pointwise(r, make_epilogue(norm1=st[nname], affine=tabs[lvl]))
             del r
             bw = self.w[block]
             s = self._conv(bw["short"], h, make_epilogue())
-            r1 = self._conv(bw["conv1"], h, make_epilogue(bias=bw["conv1"].bias, act=2), L.OUT_F32_NHWC)
-            st[block + ".norm1"] = self._saved_stat(r1)
+            r1, part = self._conv_stats(bw["conv1"], h, make_epilogue(bias=bw["conv1"].bias, act=2), True)
+            st[block + ".norm1"] = self._finalize(part, 0, 1e-8)
             h = self._pointwise(r1, make_epilogue(norm1=st[block + ".norm1"]))
             del r1
-            r2 = self._conv(bw["conv2"], h, make_epilogue(bias=bw["conv2"].bias, act=2), L.OUT_F32_NHWC)
-            st[block + ".norm2"] = self._saved_stat(r2)
-            r = self._pointwise(r2, make_epilogue(norm1=st[block + ".norm2"], res=s, res_shift=1), to_f32=True)
+            r2, part = self._conv_stats(bw["conv2"], h, make_epilogue(bias=bw["conv2"].bias, act=2), True)
+            st[block + ".norm2"] = self._finalize(part, 0, 1e-8)
+            r, rpart = self._pointwise_stats(r2, make_epilogue(norm1=st[block + ".norm2"], res=s, res_shift=1), True)
             del r2
         if not keep_samples:
             self.samples = []
@@ -601,7 +681,7 @@ class StyleEngine:
         return cache[f]
 
     @torch.no_grad()
-    def forward_frame(self, frame, kind=0, gray=True):
+    def forward_frame(self, frame, kind=0, gray=True, out=None):
         """TransformerNet.forward of test/style_network_frame.py:392-394 (Decoder.forward :341-358): every InstanceNorm takes
         its statistics from the frame itself, the six dynamic filters are predicted per frame (FilterPredictor.forward
         :53-62), AdaIN(relu4_1) follows the filters directly (:339).  gray=False is ``validation`` of
@@ -613,15 +693,18 @@ class StyleEngine:
         else:
             N, H, W, _ = frame.shape
         frame = frame.contiguous()
-        out = torch.empty((N, 3) + self.output_size(H, W), dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty((N, 3) + self.output_size(H, W), dtype=torch.float32, device=self.device)
+        else:
+            self._check_out(out, (N, 3) + self.output_size(H, W))
         tabs = self.style["tabs"]
         for i in range(N):
-            x = self._vgg("Encoder", frame[i:i + 1], kind, gray, 1, H, W, "raw")              # fp32 NHWC relu4_1
-            h = self._pointwise(x, make_epilogue(norm1=self._frame_norm(x)))
+            x, part = self._vgg("Encoder", frame[i:i + 1], kind, gray, 1, H, W, "raw+stats")   # fp32 NHWC relu4_1 + its statistics
+            h = self._pointwise(x, make_epilogue(norm1=self._finalize(part, 3, 1e-8)))
             for j, f in enumerate(FILTERS):
                 fw = self.w[f]
                 ep = make_epilogue(bias=fw["pred"].bias)
-                c_mean = self._finalize(self._stats_part(self._conv(fw["pred"], h, ep, L.OUT_F32_NHWC)), 2, 0.0)[0]
+                c_mean = self._finalize(self._conv_stats(fw["pred"], h, ep, False)[1], 2, 0.0)[0]
                 s_mean = self._style_pred_means(f)
                 wf = []
                 for q, (fcw, fcb) in enumerate(fw["fc"]):
@@ -638,21 +721,57 @@ class StyleEngine:
             for block, lvl in (("slice4", "relu3_1"), ("slice3", "relu2_1"), ("slice2", "relu1_1")):
                 bw = self.w[block]
                 s = self._conv(bw["short"], h, make_epilogue())
-                r1 = self._conv(bw["conv1"], h, make_epilogue(bias=bw["conv1"].bias, act=2), L.OUT_F32_NHWC)
-                y = self._pointwise(r1, make_epilogue(norm1=self._frame_norm(r1)))
+                r1, part = self._conv_stats(bw["conv1"], h, make_epilogue(bias=bw["conv1"].bias, act=2), False)
+                y = self._pointwise(r1, make_epilogue(norm1=self._finalize(part, 3, 1e-8)))
                 del r1
-                r2 = self._conv(bw["conv2"], y, make_epilogue(bias=bw["conv2"].bias, act=2), L.OUT_F32_NHWC)
-                r = self._pointwise(r2, make_epilogue(norm1=self._frame_norm(r2), res=s, res_shift=1), to_f32=True)
+                r2, part = self._conv_stats(bw["conv2"], y, make_epilogue(bias=bw["conv2"].bias, act=2), False)
+                r, part = self._pointwise_stats(r2, make_epilogue(norm1=self._finalize(part, 3, 1e-8), res=s, res_shift=1), False)
                 del r2
-                h = self._pointwise(r, make_epilogue(norm1=self._frame_norm(r), affine=tabs[lvl]))    # Decoder.AdaIN :311-319
+                h = self._pointwise(r, make_epilogue(norm1=self._finalize(part, 3, 1e-8), affine=tabs[lvl]))    # Decoder.AdaIN :311-319
                 del r
             self._head(h, out[i:i + 1])
         return out
 
+    @torch.no_grad()
+    def forward_frame_graphed(self, frame, kind=0, gray=True):
+        """forward_frame() replayed from a CUDA graph captured once per input shape and style: the ~90 launches of a frame-mode
+        frame (statistics, filter prediction, rrv_fold_filter rewriting the filters' weight blobs in place, convolutions) become
+        one graph launch.  Returns the graph's static output (valid until the next call)."""
+        if self.style is None:
+            raise RuntimeError("forward() before generate_style_features()")
+        key = ("frame-graph", kind, bool(gray), tuple(frame.shape), frame.dtype)
+        plan = self._plans.get(key)
+        if plan is None:
+            g_in = torch.empty_like(frame, memory_format=torch.contiguous_format)
+            g_in.copy_(frame)
+            n0 = self.lib.rrv_launch_count()
+            g_out = self.forward_frame(g_in, kind, gray)                # eager warm-up: function attributes, caches, allocator pools
+            launches = self.lib.rrv_launch_count() - n0
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self.forward_frame(g_in, kind, gray, out=g_out)
+            plan = (graph, g_in, g_out, launches)
+            self._plans[key] = plan
+            while len(self._plans) > self.MAX_PLANS:
+                self._plans.popitem(last=False)
+        else:
+            self._plans.move_to_end(key)
+        graph, g_in, g_out, launches = plan
+        g_in.copy_(frame, non_blocking=True)
+        graph.replay()
+        self.graph_launches += launches
+        return g_out
+
     def _folded(self, f, wf1, wf2):
         """The two convolutions of a KernelFilter with its predicted 32x32 matrices folded in (see _fold_filter), without
-        touching the per-clip cache."""
+        touching the per-clip cache.  Tensor-core path: one kernel rewriting this filter's preallocated blobs."""
         fw = self.w[f]
+        if self.impl_name != "ffma":
+            cache = self.__dict__.setdefault("_frame_folds", {})
+            if f not in cache or cache[f]._src[0].data_ptr() != fw["down_w"].data_ptr():
+                cache[f] = FoldedFilter(fw, self.device)
+            return cache[f].fold(wf1, wf2)
         dw = torch.matmul(wf1, fw["down_w"].reshape(32, -1)).reshape(32, 512, 3, 3)
         db = torch.mv(wf1, fw["down_b"])
         uw = torch.einsum("ojyx,ji->oiyx", fw["up_w"], wf2).contiguous()

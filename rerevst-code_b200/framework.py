@@ -173,7 +173,7 @@ class Stylization:
         graph's static output, valid until the next call."""
         if self.use_Global:
             return eng.forward_graphed(dev_u8, kind=1, post=post)
-        y = eng.forward_frame(dev_u8, kind=1, gray=True)
+        y = eng.forward_frame_graphed(dev_u8, kind=1, gray=True)
         return eng.postprocess(y, post[1], post[0])
 
     def _side_streams(self):

@@ -903,4 +903,107 @@ def test_temporal_loss_config5_512_b4(dev):
     warp(x, flow_b.to(dev)).backward(go)
     x2 = first.to(dev).requires_grad_(True)
     warp(x2, flow_b.to(dev)).backward(go.contiguous())
-    assert torch.equal(x.grad, x2.grad)
+    assert x.grad.is_contiguous() and torch.allclose(x.grad, x2.grad, rtol=1e-5, atol=1e-5)     # float atomics: order-dependent last bits
+
+
+FUSED_STAT_CASES = [
+    # N, H, W, Cin, Cout, ups  -- main-loop shapes: merged taps (Cout <= 64), CTA pairs, two Cout tiles, nearest x2, ragged edges
+    (1, 22, 70, 64, 64, 0), (2, 19, 27, 128, 256, 0), (1, 24, 40, 256, 512, 0), (1, 26, 38, 256, 128, 1),
+    (1, 16, 48, 128, 64, 1), (3, 9, 13, 512, 64, 0), (1, 33, 65, 128, 128, 0),
+]
+
+
+@pytest.mark.parametrize("case", FUSED_STAT_CASES)
+def test_conv_fused_statistics(L, dev, case):
+    """rrv_conv.stats: {sum, sum of squares, min, max} of the written values from the convolution's epilogue, against the
+    two-pass rrv_channel_stats on the tensor it wrote (frame-mode InstanceNorm, style_network_frame.py:39-43; pre-pass :59-77)."""
+    from rerevst_code_b200.engine import ConvW, make_epilogue
+    if len(_impls(L)) < 2:
+        pytest.skip("tcgen05 path not built")
+    N, H, W, Cin, Cout, ups = case
+    g = torch.Generator().manual_seed(sum(case))
+    hin, win = (H // 2, W // 2) if ups else (H, W)
+    x = torch.randn(N, Cin, hin, win, generator=g) + 0.3
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.2
+    cw = ConvW(w.to(dev), b.to(dev), ups=bool(ups))
+    xp = _to_planes(L, x.to(dev))
+    for minmax in (1, 0):
+        d = L.Conv()
+        d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = N, H, W, Cin, Cout, 3, ups
+        d.in_hi, d.in_lo = L.ptr(xp.hi), L.ptr(xp.lo)
+        d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
+        d.ep = make_epilogue(bias=cw.bias, act=2)
+        d.out_mode = L.OUT_F32_NHWC
+        out = torch.empty((N, H, W, Cout), dtype=torch.float32, device=dev)
+        d.out_f32 = out.data_ptr()
+        part = torch.empty((5, Cout), dtype=torch.float64, device=dev)
+        L.check(L.lib().rrv_stats_init(part.data_ptr(), Cout, float(N * H * W), L.stream()))
+        d.stats, d.stats_minmax = part.data_ptr(), minmax
+        L.check(L.lib().rrv_conv2d(C.byref(d), L.IMPL_TCGEN05, L.stream()))
+        L.check(L.lib().rrv_stats_sums_to_m2(part.data_ptr(), Cout, L.stream()))
+        plain = torch.empty_like(out)                            # the same convolution without statistics: same values
+        d.stats, d.out_f32 = 0, plain.data_ptr()
+        L.check(L.lib().rrv_conv2d(C.byref(d), L.IMPL_TCGEN05, L.stream()))
+        assert torch.equal(out, plain)
+        ref = torch.empty((5, Cout), dtype=torch.float64, device=dev)
+        L.check(L.lib().rrv_channel_stats(out.data_ptr(), N * H * W, Cout, ref.data_ptr(), L.stream()))
+        part, ref = part.cpu(), ref.cpu()
+        assert torch.equal(part[0], ref[0])
+        assert torch.allclose(part[1], ref[1], rtol=1e-6, atol=1e-4 * float(ref[1].abs().max()) * 1e-2)
+        assert torch.allclose(part[2], ref[2], rtol=2e-5)
+        if minmax:
+            assert torch.equal(part[3], ref[3]) and torch.equal(part[4], ref[4])
+        else:
+            assert torch.isinf(part[3]).all() and torch.isinf(part[4]).all()
+
+
+@pytest.mark.parametrize("shape", [(2, 9, 11, 64), (1, 17, 23, 128), (3, 5, 7, 512), (1, 40, 64, 256)])
+def test_pointwise_fused_statistics(L, dev, shape):
+    from rerevst_code_b200.engine import make_epilogue
+    N, H, W, Cc = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = (torch.randn(N, H, W, Cc, generator=g) * 2 + 0.5).to(dev)
+    tab = torch.stack([torch.randn(Cc, generator=g) * 0.1, torch.rand(Cc, generator=g) + 0.5, torch.full((Cc,), -1.5), torch.full((Cc,), 2.0)]).to(dev)
+    ep = make_epilogue(norm1=tab)
+    out = torch.empty_like(x)
+    part = torch.empty((5, Cc), dtype=torch.float64, device=dev)
+    L.check(L.lib().rrv_stats_init(part.data_ptr(), Cc, float(N * H * W), L.stream()))
+    L.check(L.lib().rrv_pointwise_stats(x.data_ptr(), H * W * Cc, N, H, W, Cc, C.byref(ep), L.OUT_F32_NHWC, 0, 0, out.data_ptr(),
+                                        part.data_ptr(), 1, L.stream()))
+    L.check(L.lib().rrv_stats_sums_to_m2(part.data_ptr(), Cc, L.stream()))
+    plain = torch.empty_like(x)
+    L.check(L.lib().rrv_pointwise(x.data_ptr(), H * W * Cc, N, H, W, Cc, C.byref(ep), L.OUT_F32_NHWC, 0, 0, plain.data_ptr(), L.stream()))
+    assert torch.equal(out, plain)
+    ref = torch.empty((5, Cc), dtype=torch.float64, device=dev)
+    L.check(L.lib().rrv_channel_stats(out.data_ptr(), N * H * W, Cc, ref.data_ptr(), L.stream()))
+    part, ref = part.cpu(), ref.cpu()
+    assert torch.equal(part[0], ref[0]) and torch.equal(part[3], ref[3]) and torch.equal(part[4], ref[4])
+    assert torch.allclose(part[1], ref[1], rtol=1e-5, atol=1e-3) and torch.allclose(part[2], ref[2], rtol=1e-4)
+
+
+def test_fold_filter_kernel_matches_host_fold(L, dev, state_dict):
+    """rrv_fold_filter (the KernelFilter's two 32x32 matrices folded into its convolutions on the device, straight into
+    tensor-core blobs) against the same fold done with torch and packed by rrv_pack_weights_tc: the two convolutions agree."""
+    from rerevst_code_b200.engine import INNER_PAD, ConvW, FoldedFilter, make_epilogue
+    from rerevst_code_b200.engine import StyleEngine
+    if len(_impls(L)) < 2:
+        pytest.skip("tcgen05 path not built")
+    eng = StyleEngine(dev)
+    eng.load_weights(state_dict)
+    fw = eng.w["Filter2"]
+    g = torch.Generator().manual_seed(12)
+    wf1, wf2 = (torch.randn(32, 32, generator=g) * 0.3).to(dev), (torch.randn(32, 32, generator=g) * 0.3).to(dev)
+    down, up = FoldedFilter(fw, dev).fold(wf1, wf2)
+    dw = torch.matmul(wf1, fw["down_w"].reshape(32, -1)).reshape(32, 512, 3, 3)
+    db = torch.mv(wf1, fw["down_b"])
+    uw = torch.einsum("ojyx,ji->oiyx", fw["up_w"], wf2).contiguous()
+    down_ref, up_ref = ConvW(dw, db, cout_pad=INNER_PAD), ConvW(uw, fw["up_b"], cin_pad=INNER_PAD)
+    x = _to_planes(L, torch.randn(1, 512, 20, 36, generator=g).to(dev))
+    t_a = eng._conv(down, x, make_epilogue(bias=down.bias, act=2))
+    t_b = eng._conv(down_ref, x, make_epilogue(bias=down_ref.bias, act=2))
+    ya, yb = _from_planes(L, t_a), _from_planes(L, t_b)
+    assert float((ya[:, 32:]).abs().max()) == 0.0 and rel_linf(ya.cpu(), yb.cpu()) < 2e-5
+    u_a = eng._conv(up, t_b, make_epilogue(bias=up.bias), L.OUT_F32_NHWC)
+    u_b = eng._conv(up_ref, t_b, make_epilogue(bias=up_ref.bias), L.OUT_F32_NHWC)
+    assert rel_linf(u_a.cpu(), u_b.cpu()) < 2e-5
