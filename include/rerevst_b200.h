@@ -180,6 +180,17 @@ int rrv_postprocess_bgr(const float* in, int N, int H, int W, int y0, int x0, in
 int rrv_postprocess_bgr_u8(const float* in, int N, int H, int W, int y0, int x0, int h, int w,
                            uint8_t* out, void* stream);
 
+/* ---- backward of the frozen Vgg19 loss network -------------------------------------------- */
+/* train/train.py:376-414: Loss.backward() runs first through Vgg19 (train/style_networks.py:284-314, requires_grad False), which
+ * needs data gradients only.  The data gradient of a stride-1 3x3 convolution is rrv_conv2d itself on weights with the channel
+ * axes swapped and the taps rotated by 180 degrees (repacked once by the host side); the two passes below are the rest.
+ * rrv_relu_backward: out planes [n] = (y > 0) ? g + g2 : 0 -- ReLU backward fused with the conversion to operand planes
+ *   (g, y fp32 NHWC; g2 NULL or a second gradient arriving at the same tensor, e.g. a loss tap; out_lo NULL in bf16 mode).
+ * rrv_maxpool2x2_backward: gx [N][H][W][C] from g [N][H/2][W/2][C] and the pool's input y: the first maximum of each window
+ *   in row-major order receives the gradient (ATen's choice); a dropped odd last row / column gets zero. */
+int rrv_relu_backward(const float* g, const float* g2, const float* y, int64_t n, void* out_hi, void* out_lo, void* stream);
+int rrv_maxpool2x2_backward(const float* g, const float* y, int N, int H, int W, int C, float* gx, void* stream);
+
 /* ---- statistics ------------------------------------------------------------------------ */
 /* Per-channel partial statistics of an fp32 NHWC tensor over (N,H,W):
  * part = double[5][C] = {count, sum, M2 about the local mean, min, max}.  Two passes over the

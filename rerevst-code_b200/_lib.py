@@ -51,6 +51,8 @@ SIGNATURES = {
     "rrv_tc_tune_pair": (C.c_int, [C.c_int, C.c_int]),
     "rrv_tc_tune_merge": (C.c_int, [C.c_int]),
     "rrv_pack_weights_f32": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "rrv_relu_backward": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "rrv_maxpool2x2_backward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rrv_fold_filter": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rrv_first_layer": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rrv_maxpool2x2": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),

@@ -47,6 +47,8 @@ int nchw_to_planes(const float* in, int N, int H, int W, int C, void* hi, void* 
 int postprocess_bgr(const float* in, int N, int H, int W, int y0, int x0, int h, int w, float* out, cudaStream_t st);
 int postprocess_bgr_u8(const float* in, int N, int H, int W, int y0, int x0, int h, int w, uint8_t* out, cudaStream_t st);
 int pack_weights_f32(const float* w, int Cin, int Cout, int ksize, int Cin_pad, int Cout_pad, float* out, cudaStream_t st);
+int relu_backward(const float* g, const float* g2, const float* y, long long n, void* hi, void* lo, cudaStream_t st);
+int maxpool2x2_backward(const float* g, const float* y, int N, int H, int W, int C, float* gx, cudaStream_t st);
 int fold_filter(const float* wf1, const float* wf2, const float* down_w, const float* down_b, const float* up_w, void* down_blob,
                 float* down_bias, void* up_blob, cudaStream_t st);
 int channel_stats(const float* x, long long npix, int C, double* part, cudaStream_t st);
@@ -94,6 +96,12 @@ int rrv_tc_tune_pair(int enable, int min_bn) { return tc_tune_pair(enable, min_b
 int rrv_tc_tune_merge(int enable) { return tc_tune_merge(enable); }
 int rrv_pack_weights_f32(const float* w, int Cin, int Cout, int ksize, int Cin_pad, int Cout_pad, float* out, void* stream) {
     return pack_weights_f32(w, Cin, Cout, ksize, Cin_pad, Cout_pad, out, ST(stream));
+}
+int rrv_relu_backward(const float* g, const float* g2, const float* y, int64_t n, void* out_hi, void* out_lo, void* stream) {
+    return relu_backward(g, g2, y, n, out_hi, out_lo, ST(stream));
+}
+int rrv_maxpool2x2_backward(const float* g, const float* y, int N, int H, int W, int C, float* gx, void* stream) {
+    return maxpool2x2_backward(g, y, N, H, W, C, gx, ST(stream));
 }
 int rrv_fold_filter(const float* wf1, const float* wf2, const float* down_w, const float* down_b, const float* up_w,
                     void* down_blob, float* down_bias, void* up_blob, void* stream) {

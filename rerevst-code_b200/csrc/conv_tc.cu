@@ -44,6 +44,20 @@
 #ifndef RRV_EPI_FOLD
 #define RRV_EPI_FOLD 1          // norm stages as one FMA + clamps with pre-multiplied constants
 #endif
+// Measurement-only switches (tools/build_variants.sh; results are WRONG with any of them set): what would the epilogue of the
+// merged-tap layers cost without its global stores / without the shared-memory constant loads / without the tap-combine shuffles?
+#ifndef RRV_EXP_NOSTORE
+#define RRV_EXP_NOSTORE 0
+#endif
+#ifndef RRV_EXP_NOTAB
+#define RRV_EXP_NOTAB 0
+#endif
+#ifndef RRV_EXP_NOSHFL
+#define RRV_EXP_NOSHFL 0
+#endif
+#ifndef RRV_EXP_NORES
+#define RRV_EXP_NORES 0
+#endif
 
 namespace rrv {
 
@@ -135,7 +149,7 @@ __device__ __forceinline__ void tap_offset(const TcParams& p, const TileCoord& c
 // Shared-memory table of the per-channel constants of the fused pointwise chain, one array of
 // Cout_pad floats per constant (absent stages get their identity values).
 enum { T_BIAS = 0, T_M1, T_R1, T_LO1, T_HI1, T_M2, T_R2, T_LO2, T_HI2, T_SCALE, T_SHIFT, T_COUNT };
-enum { EPI_N1 = 1, EPI_RES = 2, EPI_N2 = 4, EPI_AFF = 8, EPI_STATS = 16 };
+enum { EPI_N1 = 1, EPI_RES = 2, EPI_N2 = 4, EPI_AFF = 8, EPI_STATS = 16, EPI_HEAD = 32 };
 
 __device__ __forceinline__ void fill_epilogue_table(float* s_tab, const EpiDev& e, int Cout, int Cout_pad, int nthreads) {
     for (int ch = threadIdx.x; ch < Cout_pad; ch += nthreads) {
@@ -177,6 +191,11 @@ __device__ __forceinline__ void fill_epilogue_table(float* s_tab, const EpiDev& 
 }
 
 __device__ __forceinline__ void lds8(const float* p, float* v) {
+#if RRV_EXP_NOTAB
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.75f;
+    return;
+#endif
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
@@ -429,18 +448,24 @@ __device__ __forceinline__ void stat_flush(StatAcc& a, double* stats, int C, int
 // 32 consecutive columns of one image row, the first of them one left of the tile).
 // MODE 2 (nearest-x2 convolution, column phases merged): the chunk's two column taps b = 0, 1 sit ts columns apart; lane l is
 // input column x0 - 1 + l and the output column 2 (x0 - 1 + l) + upx is tap0[l - 1] + tap1[l] (upx = 0) or tap0[l] + tap1[l + 1].
-template <int FLAGS, int MODE>
+template <int FLAGS, int MODE, bool ST = false>
 __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e, const float* s_tab, int ts, uint32_t taddr,
                                                const PixCtx& px, int cb, int col0, int BN, bool pre = false,
                                                const uint4* pre_rh = nullptr, const uint4* pre_rl = nullptr, int upx = 0,
-                                               float* xs = nullptr) {
+                                               float* xs = nullptr, uint32_t stage = 0u, uint32_t stage_lo = 0u) {
+    // (staged stores: the caller has NOT yet waited for this warp's previous TMA store; that wait sits right before the first
+    //  st.shared below, behind the TMEM loads and the tap combine, so the store's shared-memory read overlaps them)
+    // stage != 0 (merged-tap layers, planes output): the finished 16-byte groups go to this warp's shared-memory staging rows
+    // instead of global memory; the warp's elected lane then writes the whole row with one TMA store per plane.  A per-lane
+    // 16-byte global store at a 128-byte pixel stride costs the LSU one tag per lane (32 per instruction): measured ~0.1 ms of a
+    // 0.57 ms full-resolution 64-channel layer (tools/build_variants.sh nostore).
     constexpr bool DXM = MODE == 1;
     constexpr bool STATS = FLAGS >= 0 && (FLAGS & EPI_STATS) != 0;       // xs receives the CW finished values (0 beyond Cout)
     const bool has_res = FLAGS >= 0 ? (FLAGS & EPI_RES) != 0 : e.res_hi != nullptr;
     // the residual of the whole chunk goes in flight first, ahead of the TMEM loads and the tap combine (volatile loads: the
     // compiler would otherwise sink them to their first use to save registers, and the chain then waits for L2)
     uint4 rh[CW / 8], rl[CW / 8];
-    const bool full = cb + CW <= o.Cout && col0 + CW <= BN;        // warp-uniform
+    const bool full = ST || (cb + CW <= o.Cout && col0 + CW <= BN);        // warp-uniform (staged instantiations: guaranteed by the host)
     if (pre) {                                                     // loaded by the caller while the MMAs were still running
 #pragma unroll
         for (int g = 0; g < CW / 8; ++g) {
@@ -450,6 +475,11 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
     } else if (has_res && px.valid && full) {
 #pragma unroll
         for (int g = 0; g < CW / 8; ++g) {
+#if RRV_EXP_NORES
+            rh[g] = make_uint4(0, 0, 0, 0);
+            rl[g] = make_uint4(0, 0, 0, 0);
+            continue;
+#endif
 #if RRV_EPI_RESVOL
             if (e.res_f32) {
                 const float* rf = reinterpret_cast<const float*>(e.res_hi) + px.res_off + cb + g * 8;
@@ -497,8 +527,12 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const float a = __uint_as_float(a0[i]);
+#if RRV_EXP_NOSHFL
+                const float b = __uint_as_float(a1[i]), c = __uint_as_float(a2[i]);
+#else
                 const float b = __shfl_down_sync(0xffffffffu, __uint_as_float(a1[i]), 1);
                 const float c = __shfl_down_sync(0xffffffffu, __uint_as_float(a2[i]), 2);
+#endif
                 r[16 * h + i] = __float_as_uint((a + b) + c);
             }
         }
@@ -521,8 +555,12 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
         }
     }
     if (MODE == 0) ptx::tmem_ld32_wait(r);
+    if (ST || (FLAGS == 0 && stage != 0u)) {       // warp-uniform: before any lane leaves
+        if ((threadIdx.x & 31) == 0) ptx::bulk_wait_read0();
+        __syncwarp();
+    }
     if (!STATS && !px.valid) return;       // (with statistics every lane stays for the warp-wide reduction that follows)
-    if (full && o.out_mode == RRV_OUT_PLANES) {
+    if (ST || (full && o.out_mode == RRV_OUT_PLANES)) {
         // fast path (every per-frame layer but the RGB head): no per-group range checks, planes output
         uint16_t* oh = o.out_hi + px.out_off + cb;
         uint16_t* ol = o.out_lo ? o.out_lo + px.out_off + cb : nullptr;
@@ -537,6 +575,19 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
             }
             uint4 hi, lo;
             split8(x, hi, lo);
+#if RRV_EXP_NOSTORE
+            if (hi.x != 0x7fc07fc0u || lo.y != 0x7fc17fc1u) continue;       // (never true in practice: the values stay live, nothing is stored)
+#endif
+            if (ST || (FLAGS == 0 && stage != 0u)) {      // ST: only ever staged; FLAGS 0: decided per launch; generic (FLAGS < 0): never
+                // rows of 64 bytes (the chunk's 32 channels of one pixel), SWIZZLE_64B: 16-byte piece ^= address bits 7..8;
+                // row = lane (MODE 1) or lane - 1 (MODE 2: lanes 1..30 are the tile's columns)
+                const int row = (int)(threadIdx.x & 31) - (MODE == 2 ? 1 : 0);
+                const uint32_t off = (uint32_t)(row * 64 + ((g ^ ((row >> 1) & 3)) << 4));
+                ptx::sts_v4(stage + off, hi);
+                if (ol) ptx::sts_v4(stage_lo + off, lo);
+                continue;
+            }
+            if (ST) continue;
             *reinterpret_cast<uint4*>(oh + g * 8) = hi;
             if (ol) *reinterpret_cast<uint4*>(ol + g * 8) = lo;
         }
@@ -832,6 +883,8 @@ struct Tc2Params {
     int acc_stride, set_stride, bufs, tmem_cols;
     double* stats;          // rrv_conv.stats: double[5][Cout] accumulated by the epilogue (EPI_STATS instantiations), or NULL
     int stats_minmax;
+    int ostage;             // merged-tap layers with planes output: bytes of per-warp output staging per plane (2048 | 4096), 0 = direct stores
+    int ostage_off;         // offset of the staging area (EPI_WARPS x 2 planes x ostage bytes) in dynamic shared memory
     EpiDev ep;
 };
 
@@ -847,6 +900,7 @@ template <int FLAGS, bool PAIR, bool DXM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
                 const Tc2Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t s_afull[MAX_STAGES], s_aempty[MAX_STAGES], s_bfull[MAX_B_SLOTS], s_bempty[MAX_B_SLOTS],
@@ -892,6 +946,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             ptx::prefetch_tmap(&map_a_lo);
             ptx::prefetch_tmap(&map_b_lo);
         }
+    }
+    if (p.ostage && warp == 2 && lane == 0) {
+        ptx::prefetch_tmap(&map_o_hi);
+        if (p.x3) ptx::prefetch_tmap(&map_o_lo);
     }
     float* s_tab = reinterpret_cast<float*>(smem_raw + (smem_base - ptx::smem_u32(smem_raw)) + tab_off);
     fill_epilogue_table(s_tab, p.ep, p.Cout, p.Cout_pad, TC_THREADS);
@@ -1180,6 +1238,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int ty = DXM ? quad : (m >> 3), tx = DXM ? lane : (m & 7);
         const int nchunks = (p.BNe + CW - 1) / CW;
         const EpiDev& e = p.ep;
+        // the full-chain and norm1-only merged-tap instantiations (slice2.conv2, slice2.conv1) always store through the staging rows
+        constexpr bool kStaged = DXM && (FLAGS == (EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF) || FLAGS == EPI_N1);
+        // this warp's output staging rows (hi plane, then lo plane), 1024-byte aligned
+        const uint32_t o_stage = p.ostage ? smem_base + (uint32_t)p.ostage_off + (uint32_t)((warp - 2) * 2 * p.ostage) : 0u;
         constexpr bool STATS = FLAGS >= 0 && (FLAGS & EPI_STATS) != 0;
         StatAcc sacc;
         if (STATS) {
@@ -1197,7 +1259,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const int x0 = ((t % p.tiles_x) * (PAIR ? 2 : 1) + (int)cta_rank) * cols_per_tile; t /= p.tiles_x;
             const int y0 = (t % p.tiles_y) * rows_per_set;
             const int n = t / p.tiles_y;
-            if (DXM && p.dxm == 2) {
+            // (the full-chain and statistics instantiations never run the merged-phase layout: the host sends those to the generic one)
+            constexpr bool kMode2 = DXM && FLAGS != (EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF) && FLAGS != EPI_HEAD;
+            if (kMode2 && p.dxm == 2) {
                 // nearest-x2 convolution, column phases merged: warp (quad, half) = (tile row, column phase px); lanes 1..30 are the
                 // tile's 30 low-resolution columns; output pixel (2 iy + py, 2 ix + px)
                 const int iy = y0 + quad, ix = x0 + lane - 1;
@@ -1206,9 +1270,70 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 ptx::mbar_wait(ptx::smem_u32(&s_tfull[as]), aphase);
                 ptx::tc_fence_after();
                 const uint32_t ta = tmem_base + (uint32_t)(as * p.set_stride) + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 2 * p.Cout_pad);
-                for (int c = 0; c < p.Cout_pad / CW; ++c)
-                    epilogue_chunk<FLAGS, 2>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(c * CW), px, c * CW, c * CW, p.Cout_pad, false, nullptr,
-                                             nullptr, half);
+                if (STATS) {                         // (frame mode / pre-pass: fp32 NHWC output + the statistics of what is written)
+#define RRV_STAT_CHUNK2(J)                                                                                                             \
+    if ((J) < p.Cout_pad / CW) {                                                                                                       \
+        float xs[CW];                                                                                                                  \
+        epilogue_chunk<FLAGS, 2>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)((J) * CW), px, (J) * CW, (J) * CW, p.Cout_pad, false, nullptr, \
+                                 nullptr, half, xs);                                                                                   \
+        stat_add<(J)>(sacc, xs, valid, lane, st_mm);                                                                                   \
+    }
+                    RRV_STAT_CHUNK2(0) RRV_STAT_CHUNK2(1)
+#undef RRV_STAT_CHUNK2
+                } else
+                for (int c = 0; c < p.Cout_pad / CW; ++c) {
+                    epilogue_chunk<FLAGS, 2, kStaged>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(c * CW), px, c * CW, c * CW, p.Cout_pad, false, nullptr,
+                                                      nullptr, half, nullptr, o_stage, o_stage + (uint32_t)p.ostage);
+                    if (kStaged || p.ostage) {
+                        // 30 output pixels of one column phase of one output row x 32 channels per plane: tensor view
+                        // (C, column parity, W / 2, H, N)
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0 && iy < p.in_H) {
+                            ptx::tma_store_5d(&map_o_hi, o_stage, c * CW, half, x0, 2 * iy + ph, n);
+                            if (p.o.out_lo) ptx::tma_store_5d(&map_o_lo, o_stage + (uint32_t)p.ostage, c * CW, half, x0, 2 * iy + ph, n);
+                            ptx::bulk_commit();
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (PAIR) ptx::mbar_arrive_cluster(ptx::smem_u32(&s_tempty[as]), 0u);
+                    else ptx::mbar_arrive(ptx::smem_u32(&s_tempty[as]));
+                }
+                if (++as == p.bufs) { as = 0; aphase ^= 1u; }
+                continue;
+            }
+            if constexpr (DXM && FLAGS == EPI_HEAD) {
+                // the RGB head (Decoder.slice1, 64 -> 3, bias only): three useful accumulator columns per tap.  One warp per tile row
+                // loads 4 columns of each tap, combines the taps of its 3 channels and writes the pixel (NCHW or the finished BGR
+                // frame); nothing else of the generic chunk machinery runs.
+                const int iy = y0 + quad, ix = x0 + lane;
+                const bool valid = iy < p.in_H && ix < p.in_W && lane < 30;
+                const PixCtx px = make_pix(p.o, e, n, iy, ix, valid);
+                ptx::mbar_wait(ptx::smem_u32(&s_tfull[as]), aphase);
+                ptx::tc_fence_after();
+                if (half == 0) {
+                    const uint32_t ta = tmem_base + (uint32_t)(as * p.set_stride) + ((uint32_t)(quad * 32) << 16);
+                    uint32_t a0[4], a1[4], a2[4];
+                    ptx::tmem_ld4_issue(ta, a0);
+                    ptx::tmem_ld4_issue(ta + (uint32_t)p.Cout_pad, a1);
+                    ptx::tmem_ld4_issue(ta + (uint32_t)(2 * p.Cout_pad), a2);
+                    ptx::tmem_ld4_wait(a0);
+                    ptx::tmem_ld4_wait(a1);
+                    ptx::tmem_ld4_wait(a2);
+                    float x[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) x[c] = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float b1 = __shfl_down_sync(0xffffffffu, __uint_as_float(a1[c]), 1);
+                        const float b2 = __shfl_down_sync(0xffffffffu, __uint_as_float(a2[c]), 2);
+                        x[c] = ((__uint_as_float(a0[c]) + b1) + b2) + s_tab[T_BIAS * p.Cout_pad + c];
+                    }
+                    if (valid) store_group<true>(p.o, x, px, 0, p.o.Cout < 4 ? p.o.Cout : 4);
+                }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -1223,7 +1348,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const bool has_res = FLAGS >= 0 ? kHasResStatic : e.res_hi != nullptr;
             uint4 pre_rh[CW / 8], pre_rl[CW / 8];
             bool pre = false;
-            if (RRV_EPI_PREFETCH && has_res) {
+            if (RRV_EPI_PREFETCH && has_res && !RRV_EXP_NORES) {
                 const int iy = y0 + ty, ix = x0 + tx;
                 const bool valid = iy < p.in_H && ix < p.in_W && (!DXM || tx < 30);
                 const int oy = p.nph == 4 ? 2 * iy + (ph >> 1) : iy;
@@ -1287,6 +1412,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     st_n0 = n0;
                     continue;
                 }
+                if (DXM && (kStaged || (FLAGS == 0 && p.ostage))) {  // (one chunk per warp: Cout_pad <= 64)
+                    if (half < nchunks)
+                        epilogue_chunk<FLAGS, 1, kStaged>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(half * CW), px, n0 + half * CW, half * CW, p.BNe,
+                                                          pre && mt == 0, pre_rh, pre_rl, 0, nullptr, o_stage, o_stage + (uint32_t)p.ostage);
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && half < nchunks && iy < p.in_H) {      // this warp's row: 30 pixels x its 32 channels per plane
+                        ptx::tma_store_4d(&map_o_hi, o_stage, half * CW, x0, iy, n);
+                        if (p.o.out_lo) ptx::tma_store_4d(&map_o_lo, o_stage + (uint32_t)p.ostage, half * CW, x0, iy, n);
+                        ptx::bulk_commit();
+                    }
+                    continue;
+                }
                 for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4)
                     epilogue_chunk<FLAGS, DXM ? 1 : 0>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, ch * CW, p.BNe,
                                                pre && mt == 0 && ch == half, pre_rh, pre_rl);
@@ -1305,11 +1443,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             }
             if (++as == p.bufs) { as = 0; aphase ^= 1u; }
         }
+        if (p.ostage && lane == 0) ptx::bulk_wait0();    // this lane's TMA stores have completed before the CTA's shared memory goes away
         if (STATS && p.n_ntiles == 1) {              // one Cout tile: the lane-to-channel map never changed, one flush per kernel
-            stat_flush<0>(sacc, p.stats, p.Cout, (half + 0) * CW + lane, st_mm);
-            stat_flush<1>(sacc, p.stats, p.Cout, (half + 2) * CW + lane, st_mm);
-            stat_flush<2>(sacc, p.stats, p.Cout, (half + 4) * CW + lane, st_mm);
-            stat_flush<3>(sacc, p.stats, p.Cout, (half + 6) * CW + lane, st_mm);
+            const bool m2 = DXM && p.dxm == 2;       // merged phases: a warp owns chunks 0, 1 (slot = chunk), else chunks half, half + 2, ...
+            stat_flush<0>(sacc, p.stats, p.Cout, (m2 ? 0 : half + 0) * CW + lane, st_mm);
+            stat_flush<1>(sacc, p.stats, p.Cout, (m2 ? 1 : half + 2) * CW + lane, st_mm);
+            if (!m2) {
+                stat_flush<2>(sacc, p.stats, p.Cout, (half + 4) * CW + lane, st_mm);
+                stat_flush<3>(sacc, p.stats, p.Cout, (half + 6) * CW + lane, st_mm);
+            }
         }
     }
 
@@ -1408,6 +1550,36 @@ int encode_w_map(CUtensorMap* m, const void* base, int rows, int Cin, int BN) {
     return 0;
 }
 
+// Output planes [N][H][W][C] for the staged TMA stores of the merged-tap layers.
+//   mode 1: box = 32 channels x 30 pixels of one row, rows of 64 bytes, SWIZZLE_64B (one epilogue warp's share of a tile row);
+//   mode 2: the tensor seen as (C, column parity, W / 2, H, N): box = 32 channels x 1 parity x 30 low-res columns, SWIZZLE_64B
+//           (one 32-channel chunk of one column phase of one output row of the nearest-x2 convolution).
+int encode_out_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int mode) {
+    CUresult r;
+    if (mode == 1) {
+        const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        const cuuint32_t box[4] = {32, 30, 1, 1};
+        const cuuint32_t es[4] = {1, 1, 1, 1};
+        r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        const cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)(W / 2), (cuuint64_t)H, (cuuint64_t)N};
+        const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 4, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        const cuuint32_t box[5] = {32, 1, 30, 1, 1};
+        const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+        r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(output %dx%dx%dx%d, mode %d) failed: %d", N, H, W, C, mode, (int)r);
+        return 1;
+    }
+    return 0;
+}
+
 int cout_pad_of(int Cout) { return (Cout + 15) / 16 * 16; }
 
 OutDesc make_out(const rrv_conv* p) {
@@ -1455,6 +1627,10 @@ int launch_tc1(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, co
     return check_launch("conv_tc_kernel");
 }
 
+// (the two output maps of the staged TMA stores travel in file-scope slots set by conv2d_tc2 right before the launch: every
+//  launch helper below forwards them without growing its signature)
+static thread_local CUtensorMap t_mo_hi, t_mo_lo;
+
 template <int FLAGS, bool PAIR, bool DXM>
 int launch_tc2p(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
                 const CUtensorMap& mb_lo, const Tc2Params& d) {
@@ -1486,7 +1662,7 @@ int launch_tc2p(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, c
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<FLAGS, PAIR, DXM>, ma_hi, ma_lo, mb_hi, mb_lo, d);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc2_kernel<FLAGS, PAIR, DXM>, ma_hi, ma_lo, mb_hi, mb_lo, t_mo_hi, t_mo_lo, d);
     RRV_REQUIRE(e == cudaSuccess, "cudaLaunchKernelEx(conv_tc2_kernel%s): %s", PAIR ? ", cluster 2" : "", cudaGetErrorString(e));
     return check_launch("conv_tc2_kernel");
 }
@@ -1525,10 +1701,26 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     d.dxm = (g_tune.dxm && p->ksize == 3 && !ups && 3 * d.Cout_pad <= 256 && d.in_W >= 16) ? 1 : 0;
     static const bool no_ups_merge = getenv("RRV_NO_UPS_MERGE") != nullptr;      // A/B switch for measurements
     if (!no_ups_merge && g_tune.dxm && p->ksize == 3 && ups && 4 * d.Cout_pad <= 256 && d.Cout_pad % CW == 0 && d.in_W >= 16 &&
-        p->out_mode == RRV_OUT_PLANES && p->stats == nullptr)
+        (p->out_mode == RRV_OUT_PLANES || (p->out_mode == RRV_OUT_F32_NHWC && p->stats != nullptr && p->Cout == d.Cout_pad)))
         d.dxm = 2;
     const int xchg_bytes = (p->pool && d.dxm) ? EPI_WARPS * 512 : 0;       // row-partner exchange of the fused max-pool
-    const int budget = SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES - xchg_bytes;
+    // merged-tap layers writing planes: per-warp output staging + TMA stores (see epilogue_chunk); RRV_NO_OSTAGE=1 is the A/B switch
+    static const bool no_ostage = getenv("RRV_NO_OSTAGE") != nullptr;
+    d.ostage = 0;
+    if (!no_ostage && d.dxm && p->out_mode == RRV_OUT_PLANES && !p->pool && p->stats == nullptr && p->Cout == d.Cout_pad) {
+        const int fl = epi_flags(p->ep);             // the instantiations that carry the staging code
+        if (d.dxm == 1 && p->Cout % CW == 0 && (fl == 0 || fl == (EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF))) d.ostage = 2048;
+        if (d.dxm == 2 && p->Cout == 64 && fl == EPI_N1) d.ostage = 2048;
+    }
+    if (d.ostage) {      // the staging rows must leave room for two A stages and two weight slots (CTA pairs halve the weight slots)
+        const bool pair_ok = g_tune.pair && num_sms() % 2 == 0;
+        const int bn = (d.dxm == 2 ? 4 : 3) * d.Cout_pad;
+        const bool pr = d.dxm == 2 ? pair_ok : (pair_ok && bn >= std::min(g_tune.pair_min_bn, 48) && (bn / 2) % 8 == 0);
+        const int need = 2 * planes * (d.dxm == 2 ? 5 : 6) * 4096 + 2 * planes * bn * 128 / (pr ? 2 : 1);
+        if (need > SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES - xchg_bytes - (EPI_WARPS * 2 * d.ostage + 1024)) d.ostage = 0;
+    }
+    const int ostage_bytes = d.ostage ? EPI_WARPS * 2 * d.ostage + 1024 : 0;
+    const int budget = SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES - xchg_bytes - ostage_bytes;
     if (d.dxm == 2) {
         // ---- nearest-x2 convolution with Cout <= 64 (ResidualBlock slice2.conv1): per output parity the 3x3 convolution is a 2x2
         //      convolution over the low-resolution input.  With N = Cout = 64 an MMA costs the A fetch (64 cycles) however small N is,
@@ -1719,7 +1911,18 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         ma_lo = ma_hi;
         mb_lo = mb_hi;
     }
-    const int smem = d.a_stages * a_stage + d.b_slots * b_slot + d.Cout_pad * TAB_BYTES + xchg_bytes + 1024;
+    d.ostage_off = (d.a_stages * a_stage + d.b_slots * b_slot + d.Cout_pad * TAB_BYTES + xchg_bytes + 1023) / 1024 * 1024;
+    memset(&t_mo_hi, 0, sizeof(t_mo_hi));
+    memset(&t_mo_lo, 0, sizeof(t_mo_lo));
+    if (d.ostage) {
+        if (encode_out_map(&t_mo_hi, p->out_hi, d.N, d.o.H, d.o.W, p->Cout, d.dxm)) return 1;
+        if (p->out_lo) {
+            if (encode_out_map(&t_mo_lo, p->out_lo, d.N, d.o.H, d.o.W, p->Cout, d.dxm)) return 1;
+        } else {
+            t_mo_lo = t_mo_hi;
+        }
+    }
+    const int smem = d.a_stages * a_stage + d.b_slots * b_slot + d.Cout_pad * TAB_BYTES + xchg_bytes + ostage_bytes + 1024;
     // the specialised instantiations write planes / NHWC only; NCHW and the finished BGR frame (the RGB head) take the generic one
     const bool plain_out = p->out_mode == RRV_OUT_PLANES || p->out_mode == RRV_OUT_F32_NHWC;
     const int flags = plain_out ? epi_flags(p->ep) : -1;
@@ -1731,10 +1934,16 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         }
         return launch_tc2<EPI_STATS>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
     }
+    if (d.dxm == 1 && !plain_out && p->Cout <= 4 && epi_flags(p->ep) == 0 && p->ep.act == 0 && !p->pool) {     // the RGB head
+        if (d.pair) return launch_tc2p<EPI_HEAD, true, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+        return launch_tc2p<EPI_HEAD, false, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
+    }
     if (d.dxm) {
-        // merged-tap layers: conv1_2 (bias + ReLU [+ pool]), slice2.conv2 (the full chain), the RGB head / anything else (generic)
-        const int f = (flags == 0 || flags == (EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF)) ? flags : -1;      // (flags < 0 stays generic)
-        if (flags == EPI_N1) {          // slice2.conv1 (merged column phases)
+        // merged-tap layers: conv1_2 (bias + ReLU [+ pool]), slice2.conv2 (the full chain), the RGB head / anything else (generic).
+        // The full-chain and norm1-only instantiations store through the staging rows only: without staging, the generic one.
+        int f = (flags == 0 || flags == (EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF)) ? flags : -1;      // (flags < 0 stays generic)
+        if (f > 0 && (!d.ostage || d.dxm == 2)) f = -1;
+        if (flags == EPI_N1 && d.ostage) {          // slice2.conv1 (merged column phases)
             if (d.pair) return launch_tc2p<EPI_N1, true, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
             return launch_tc2p<EPI_N1, false, true>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
         }

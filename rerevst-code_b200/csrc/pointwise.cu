@@ -59,31 +59,88 @@ int maxpool2x2(const void* in_hi, const void* in_lo, int N, int H, int W, int C,
 }
 
 // ---- epilogue chain alone over fp32 NHWC ----
-// STATS: the per-channel {sum, sum of squares[, min, max]} of the values written also go to `stats` (double[5][C]).  A thread keeps
-// one 8-channel group for the whole kernel (the grid stride is a multiple of C / 8), sums its pixels in fp32 (a few dozen values),
-// the block combines the threads of equal group in double through shared memory and issues one atomic per channel and quantity.
+// A thread keeps ONE 8-channel group for the whole kernel (the grid stride is a multiple of C / 8) and walks over pixels: the
+// per-channel constants of the chain are loaded into registers once, the index math is 32-bit, and per pixel there are two 16-byte
+// loads (+ the residual), ~10 FP32 operations per value, the hi / lo split and two 16-byte stores -- an HBM-bound pass.
+// STATS: the per-channel {sum, sum of squares[, min, max]} of the values written also go to `stats` (double[5][C]): fp32 per thread
+// (a few dozen pixels), then double across the block's threads of equal group through shared memory, one atomic per channel.
 template <bool STATS>
 __global__ void __launch_bounds__(256) pointwise_kernel(const float* __restrict__ in, long long in_bs, int N, int H, int W,
                                                         int C, EpiDev ep, int out_mode, uint16_t* out_hi,
                                                         uint16_t* out_lo, float* out_f32, double* stats, int stats_minmax) {
     const int C8 = C >> 3;
-    const long long total = (long long)N * H * W * C8;
+    const unsigned gtid = blockIdx.x * 256u + threadIdx.x, gthreads = gridDim.x * 256u;
+    const int c0 = (int)(gtid % (unsigned)C8) * 8;
+    const unsigned pstride = gthreads / (unsigned)C8;
+    const unsigned HW = (unsigned)H * (unsigned)W, npix = (unsigned)N * HW;
     float ssum[8], ssq[8], smn[8], smx[8];
     if (STATS) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) { ssum[k] = 0.0f; ssq[k] = 0.0f; smn[k] = CUDART_INF_F; smx[k] = -CUDART_INF_F; }
     }
-    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-        const int c0 = (int)(i % C8) * 8;
-        long long t = i / C8;
-        const int x = (int)(t % W); t /= W;
-        const int y = (int)(t % H);
-        const int n = (int)(t / H);
-        const float* src = in + (long long)n * in_bs + ((long long)y * W + x) * C + c0;
-        float v[8];
-        const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        apply_epilogue<8>(ep, v, n, y, x, c0);
+    // per-channel constants, once per thread
+    float bias[8], m1[8], r1[8], lo1[8], hi1[8], m2[8], r2[8], lo2[8], hi2[8], sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        bias[k] = ep.bias ? __ldg(ep.bias + c) : 0.0f;
+        m1[k] = ep.norm1 ? __ldg(ep.norm1 + c) : 0.0f;
+        r1[k] = ep.norm1 ? __ldg(ep.norm1 + C + c) : 1.0f;
+        lo1[k] = ep.norm1 ? __ldg(ep.norm1 + 2 * C + c) : -CUDART_INF_F;
+        hi1[k] = ep.norm1 ? __ldg(ep.norm1 + 3 * C + c) : CUDART_INF_F;
+        m2[k] = ep.norm2 ? __ldg(ep.norm2 + c) : 0.0f;
+        r2[k] = ep.norm2 ? __ldg(ep.norm2 + C + c) : 1.0f;
+        lo2[k] = ep.norm2 ? __ldg(ep.norm2 + 2 * C + c) : -CUDART_INF_F;
+        hi2[k] = ep.norm2 ? __ldg(ep.norm2 + 3 * C + c) : CUDART_INF_F;
+        sc[k] = ep.affine ? __ldg(ep.affine + c) : 1.0f;
+        sh[k] = ep.affine ? __ldg(ep.affine + C + c) : 0.0f;
+    }
+    for (unsigned p = gtid / (unsigned)C8; p < npix; p += pstride) {
+        unsigned n = 0, rem = p;
+        if (N > 1) { n = p / HW; rem = p - n * HW; }
+        const float* src = in + (long long)n * in_bs + (long long)rem * C + c0;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        float rr[8];
+        if (ep.res_hi != nullptr) {
+            const unsigned y = rem / (unsigned)W, x = rem - y * (unsigned)W;
+            const long long off = (long long)n * ep.res_batch_stride + ((long long)(y >> ep.res_shift) * ep.res_W + (x >> ep.res_shift)) * C + c0;
+            if (ep.res_f32) {
+                const float* rf = reinterpret_cast<const float*>(ep.res_hi) + off;
+                const float4 q0 = __ldg(reinterpret_cast<const float4*>(rf)), q1 = __ldg(reinterpret_cast<const float4*>(rf + 4));
+                rr[0] = q0.x; rr[1] = q0.y; rr[2] = q0.z; rr[3] = q0.w; rr[4] = q1.x; rr[5] = q1.y; rr[6] = q1.z; rr[7] = q1.w;
+            } else {
+                load8(ep.res_hi + off, ep.res_lo ? ep.res_lo + off : nullptr, ep.lo_fp16, rr);
+            }
+        }
+        // the chain of rrv_epilogue, in the reference's operation order (rrv_common.cuh: apply_epilogue)
+        if (ep.bias != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += bias[k];
+        }
+        if (ep.act == 1) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.0f);
+        } else if (ep.act == 2) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.0f ? v[k] : 0.2f * v[k];
+        }
+        if (ep.norm1 != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fminf(hi1[k], fmaxf(lo1[k], (v[k] - m1[k]) * r1[k]));
+        }
+        if (ep.res_hi != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += rr[k];
+        }
+        if (ep.norm2 != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = fminf(hi2[k], fmaxf(lo2[k], (v[k] - m2[k]) * r2[k]));
+        }
+        if (ep.affine != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = v[k] * sc[k] + sh[k];
+        }
         if (STATS) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -93,7 +150,7 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const float* __restrict_
                 smx[k] = fmaxf(smx[k], v[k]);
             }
         }
-        const long long o = (((long long)n * H + y) * W + x) * C + c0;
+        const long long o = (long long)p * C + c0;
         if (out_mode == RRV_OUT_PLANES) {
             store8(out_hi + o, out_lo ? out_lo + o : nullptr, ep.lo_fp16, v);
         } else {
@@ -111,18 +168,17 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const float* __restrict_
         const int groups = C8 < 256 ? C8 : 256;
         for (int j = t; j < groups * 8; j += 256) {
             const int g = j >> 3, k = j & 7;
-            double a = 0.0, b = 0.0;
+            double sa = 0.0, sb = 0.0;
             float mn = CUDART_INF_F, mx = -CUDART_INF_F;
             for (int u = g; u < 256; u += groups) {
-                a += (double)s_red[0][u][k];
-                b += (double)s_red[1][u][k];
+                sa += (double)s_red[0][u][k];
+                sb += (double)s_red[1][u][k];
                 mn = fminf(mn, s_red[2][u][k]);
                 mx = fmaxf(mx, s_red[3][u][k]);
             }
-            // which channel group does thread g own?  i = blockIdx.x * 256 + g (+ multiples of the stride): c0 = (i % C8) * 8
-            const int c = (int)(((long long)blockIdx.x * 256 + g) % C8) * 8 + k;
-            atomicAdd(stats + C + c, a);
-            atomicAdd(stats + 2 * C + c, b);
+            const int c = (int)((blockIdx.x * 256u + (unsigned)g) % (unsigned)C8) * 8 + k;      // the group thread g of this block owns
+            atomicAdd(stats + C + c, sa);
+            atomicAdd(stats + 2 * C + c, sb);
             if (stats_minmax) {
                 atomic_min_double(stats + 3 * C + c, (double)mn);
                 atomic_max_double(stats + 4 * C + c, (double)mx);
@@ -139,9 +195,10 @@ int pointwise(const float* in, long long in_bs, int N, int H, int W, int C, cons
     RRV_REQUIRE(out_mode == RRV_OUT_PLANES ? out_hi != nullptr : out_f32 != nullptr, "rrv_pointwise: NULL output");
     const long long total = (long long)N * H * W * (C / 8);
     if (total == 0) return 0;
-    const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+    RRV_REQUIRE((long long)N * H * W < (1LL << 31), "rrv_pointwise: more than 2^31 pixels");
+    RRV_REQUIRE(C / 8 <= 256 && 256 % (C / 8) == 0, "rrv_pointwise: C / 8 must divide 256 (C=%d)", C);     // a thread keeps its channel group
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 8);
     if (stats != nullptr) {
-        RRV_REQUIRE(C <= 2048 && 256 % (C / 8 < 256 ? C / 8 : 256) == 0 && (C / 8 <= 256), "rrv_pointwise_stats: C / 8 must divide 256 (C=%d)", C);
         pointwise_kernel<true><<<grid, 256, 0, st>>>(in, in_bs, N, H, W, C, make_epi(*ep, C), out_mode, (uint16_t*)out_hi,
                                                      (uint16_t*)out_lo, out_f32, stats, stats_minmax);
         return check_launch("pointwise_kernel<stats>");
@@ -364,6 +421,94 @@ int fold_filter(const float* wf1, const float* wf2, const float* down_w, const f
     RRV_REQUIRE(wf1 && wf2 && down_w && down_b && up_w && down_blob && down_bias && up_blob, "rrv_fold_filter: NULL tensor");
     fold_filter_kernel<<<148 * 4, 256, 0, st>>>(wf1, wf2, down_w, down_b, up_w, (uint16_t*)down_blob, down_bias, (uint16_t*)up_blob);
     return check_launch("fold_filter_kernel");
+}
+
+}  // namespace rrv
+
+// ---- backward pieces of the frozen Vgg19 loss network (train/style_networks.py:284-314; train.py:376-414) ---------------
+// Loss.backward() first runs through Vgg19 (requires_grad = False: only data gradients).  The data gradient of a 3x3
+// convolution is the same implicit GEMM with transposed, 180-degree rotated weights (packed once on the host side, then
+// rrv_conv2d); what remains are these two memory-bound passes.
+namespace rrv {
+
+// ReLU backward fused with the conversion to operand planes: out = (y > 0) ? g (+ g2) : 0.
+// g: gradient w.r.t. the ReLU output (fp32 NHWC); g2: optional second gradient arriving at the same tensor (a loss tap);
+// y: the ReLU output saved by the forward pass.
+__global__ void __launch_bounds__(256) relu_backward_kernel(const float* __restrict__ g, const float* __restrict__ g2,
+                                                            const float* __restrict__ y, long long n8, uint16_t* __restrict__ hi,
+                                                            uint16_t* __restrict__ lo) {
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+        const float4 a0 = *reinterpret_cast<const float4*>(g + i * 8), a1 = *reinterpret_cast<const float4*>(g + i * 8 + 4);
+        const float4 y0 = *reinterpret_cast<const float4*>(y + i * 8), y1 = *reinterpret_cast<const float4*>(y + i * 8 + 4);
+        float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const float m[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+        if (g2 != nullptr) {
+            const float4 b0 = *reinterpret_cast<const float4*>(g2 + i * 8), b1 = *reinterpret_cast<const float4*>(g2 + i * 8 + 4);
+            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = m[k] > 0.0f ? v[k] : 0.0f;
+        store8(hi + i * 8, lo ? lo + i * 8 : nullptr, 0, v);
+    }
+}
+
+int relu_backward(const float* g, const float* g2, const float* y, long long n, void* hi, void* lo, cudaStream_t st) {
+    RRV_REQUIRE(g && y && hi, "rrv_relu_backward: NULL tensor");
+    RRV_REQUIRE(n % 8 == 0, "rrv_relu_backward: element count must be a multiple of 8");
+    if (n == 0) return 0;
+    const int grid = (int)std::min<long long>((n / 8 + 255) / 256, 148LL * 32);
+    relu_backward_kernel<<<grid, 256, 0, st>>>(g, g2, y, n / 8, (uint16_t*)hi, (uint16_t*)lo);
+    return check_launch("relu_backward_kernel");
+}
+
+// nn.MaxPool2d(2, 2) backward: the gradient of a pooled pixel goes to the first maximum of its 2x2 window in row-major order
+// (ATen's max_pool2d_with_indices picks the same one); a dropped odd last row / column gets zero.
+__global__ void __launch_bounds__(256) maxpool_backward_kernel(const float* __restrict__ g, const float* __restrict__ y, int N, int H,
+                                                               int W, int C, float* __restrict__ gx) {
+    const int C4 = C >> 2;
+    const long long total = (long long)N * H * W * C4;
+    const int Ho = H >> 1, Wo = W >> 1;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const int c = (int)(i % C4) * 4;
+        long long t = i / C4;
+        const int x = (int)(t % W); t /= W;
+        const int yy = (int)(t % H);
+        const int n = (int)(t / H);
+        float4 out = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const int yo = yy >> 1, xo = x >> 1;
+        if (yo < Ho && xo < Wo) {
+            const float4 go = *reinterpret_cast<const float4*>(g + (((long long)n * Ho + yo) * Wo + xo) * C + c);
+            float4 w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                w[k] = *reinterpret_cast<const float4*>(y + (((long long)n * H + 2 * yo + (k >> 1)) * W + 2 * xo + (k & 1)) * C + c);
+            const int me = ((yy & 1) << 1) | (x & 1);
+            const float* wf = reinterpret_cast<const float*>(w);
+            const float gof[4] = {go.x, go.y, go.z, go.w};
+            float o4[4];
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+                int best = 0;
+                float bv = wf[ch];
+#pragma unroll
+                for (int k = 1; k < 4; ++k)
+                    if (wf[k * 4 + ch] > bv) { bv = wf[k * 4 + ch]; best = k; }
+                o4[ch] = best == me ? gof[ch] : 0.0f;
+            }
+            out = make_float4(o4[0], o4[1], o4[2], o4[3]);
+        }
+        *reinterpret_cast<float4*>(gx + i * 4) = out;
+    }
+}
+
+int maxpool2x2_backward(const float* g, const float* y, int N, int H, int W, int C, float* gx, cudaStream_t st) {
+    RRV_REQUIRE(g && y && gx, "rrv_maxpool2x2_backward: NULL tensor");
+    RRV_REQUIRE(C % 4 == 0, "rrv_maxpool2x2_backward: C must be a multiple of 4");
+    const long long total = (long long)N * H * W * (C / 4);
+    if (total == 0) return 0;
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 32);
+    maxpool_backward_kernel<<<grid, 256, 0, st>>>(g, y, N, H, W, C, gx);
+    return check_launch("maxpool_backward_kernel");
 }
 
 }  // namespace rrv

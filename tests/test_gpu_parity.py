@@ -945,7 +945,9 @@ def test_conv_fused_statistics(L, dev, case):
         plain = torch.empty_like(out)                            # the same convolution without statistics: same values
         d.stats, d.out_f32 = 0, plain.data_ptr()
         L.check(L.lib().rrv_conv2d(C.byref(d), L.IMPL_TCGEN05, L.stream()))
-        assert torch.equal(out, plain)
+        # same arithmetic; the nearest-x2 layer with Cout <= 64 takes the merged-phase main loop when statistics are requested
+        # (partial sums meet in the epilogue instead of in TMEM: last-bit differences)
+        assert torch.equal(out, plain) or (ups and Cout <= 64 and torch.allclose(out, plain, rtol=1e-5, atol=1e-6))
         ref = torch.empty((5, Cout), dtype=torch.float64, device=dev)
         L.check(L.lib().rrv_channel_stats(out.data_ptr(), N * H * W, Cout, ref.data_ptr(), L.stream()))
         part, ref = part.cpu(), ref.cpu()

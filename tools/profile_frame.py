@@ -17,25 +17,28 @@ ap.add_argument("--size", default="1080p")
 ap.add_argument("--precision", default="x3")
 ap.add_argument("--kernels", default="auto")
 ap.add_argument("--frames", type=int, default=1)
+ap.add_argument("--mode", default="global", choices=["global", "frame"], help="frame: use_Global=False (style_network_frame.py)")
 args = ap.parse_args()
 
 h, w = bench.SIZES[args.size]
 ph, pw = bench.padded_size(h, w)
-fw = Stylization(synthetic_state_dict(0), cuda=True, precision=args.precision, impl=args.kernels)
+fw = Stylization(synthetic_state_dict(0), cuda=True, precision=args.precision, impl=args.kernels, use_Global=args.mode == "global")
 fw.prepare_style(bench.synthetic_frame(512, 512, 1))
-fw.clean()
-for i in range(2):
-    fw.add(bench.synthetic_frame(h, w, 50 + i))
-fw.compute()
+if args.mode == "global":
+    fw.clean()
+    for i in range(2):
+        fw.add(bench.synthetic_frame(h, w, 50 + i))
+    fw.compute()
 eng = fw.model._eng()
 frames = [torch.from_numpy(bench.reflect_pad(bench.synthetic_frame(h, w, 100 + i), ph, pw)).unsqueeze(0).cuda() for i in range(2)]
-out = torch.empty((1, 3, ph, pw), dtype=torch.float32, device="cuda")
+post = ("f32", (64, 64, h, w))          # the finished frame, as bench.py times it
+run = (lambda f: eng.forward(f, kind=1, post=post)) if args.mode == "global" else (lambda f: eng.forward_frame(f, kind=1))
 for i in range(3):
-    eng.forward(frames[i % 2], kind=1, out=out)
+    run(frames[i % 2])
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
 for i in range(args.frames):
-    eng.forward(frames[i % 2], kind=1, out=out)
+    run(frames[i % 2])
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStop()
 print("profiled", args.frames, "frame(s) at", ph, "x", pw)
