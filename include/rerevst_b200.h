@@ -154,7 +154,7 @@ int rrv_first_layer(const void* src, int src_kind, int gray, int N, int H, int W
 int rrv_maxpool2x2(const void* in_hi, const void* in_lo, int N, int H, int W, int C,
                    void* out_hi, void* out_lo, void* stream);
 /* The epilogue chain alone over an fp32 NHWC tensor (pre-pass: normalise after the global
- * statistics are known).  in_batch_stride == 0 broadcasts one input over the batch (quirk Q1,
+ * statistics are known).  C / 4 must divide 256 (C = 32, 64, 128, 256, 512, 1024: a thread keeps one channel group).  in_batch_stride == 0 broadcasts one input over the batch (quirk Q1,
  * KernelFilter.compute :223-230).  Output per out_mode (planes or fp32 NHWC). */
 int rrv_pointwise(const float* in, int64_t in_batch_stride, int N, int H, int W, int C,
                   const rrv_epilogue* ep, int out_mode, void* out_hi, void* out_lo, float* out_f32,

@@ -68,20 +68,21 @@ template <bool STATS>
 __global__ void __launch_bounds__(256) pointwise_kernel(const float* __restrict__ in, long long in_bs, int N, int H, int W,
                                                         int C, EpiDev ep, int out_mode, uint16_t* out_hi,
                                                         uint16_t* out_lo, float* out_f32, double* stats, int stats_minmax) {
-    const int C8 = C >> 3;
+    constexpr int V = 4;                      // channels per thread: 16-byte loads, and the constants below fit ~90 registers
+    const int CV = C / V;
     const unsigned gtid = blockIdx.x * 256u + threadIdx.x, gthreads = gridDim.x * 256u;
-    const int c0 = (int)(gtid % (unsigned)C8) * 8;
-    const unsigned pstride = gthreads / (unsigned)C8;
+    const int c0 = (int)(gtid % (unsigned)CV) * V;
+    const unsigned pstride = gthreads / (unsigned)CV;
     const unsigned HW = (unsigned)H * (unsigned)W, npix = (unsigned)N * HW;
-    float ssum[8], ssq[8], smn[8], smx[8];
+    float ssum[V], ssq[V], smn[V], smx[V];
     if (STATS) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { ssum[k] = 0.0f; ssq[k] = 0.0f; smn[k] = CUDART_INF_F; smx[k] = -CUDART_INF_F; }
+        for (int k = 0; k < V; ++k) { ssum[k] = 0.0f; ssq[k] = 0.0f; smn[k] = CUDART_INF_F; smx[k] = -CUDART_INF_F; }
     }
     // per-channel constants, once per thread
-    float bias[8], m1[8], r1[8], lo1[8], hi1[8], m2[8], r2[8], lo2[8], hi2[8], sc[8], sh[8];
+    float bias[V], m1[V], r1[V], lo1[V], hi1[V], m2[V], r2[V], lo2[V], hi2[V], sc[V], sh[V];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < V; ++k) {
         const int c = c0 + k;
         bias[k] = ep.bias ? __ldg(ep.bias + c) : 0.0f;
         m1[k] = ep.norm1 ? __ldg(ep.norm1 + c) : 0.0f;
@@ -95,55 +96,60 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const float* __restrict_
         sc[k] = ep.affine ? __ldg(ep.affine + c) : 1.0f;
         sh[k] = ep.affine ? __ldg(ep.affine + C + c) : 0.0f;
     }
-    for (unsigned p = gtid / (unsigned)C8; p < npix; p += pstride) {
+    for (unsigned p = gtid / (unsigned)CV; p < npix; p += pstride) {
         unsigned n = 0, rem = p;
         if (N > 1) { n = p / HW; rem = p - n * HW; }
-        const float* src = in + (long long)n * in_bs + (long long)rem * C + c0;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
-        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        float rr[8];
+        const float4 a = __ldg(reinterpret_cast<const float4*>(in + (long long)n * in_bs + (long long)rem * C + c0));
+        float v[V] = {a.x, a.y, a.z, a.w};
+        float rr[V];
         if (ep.res_hi != nullptr) {
             const unsigned y = rem / (unsigned)W, x = rem - y * (unsigned)W;
             const long long off = (long long)n * ep.res_batch_stride + ((long long)(y >> ep.res_shift) * ep.res_W + (x >> ep.res_shift)) * C + c0;
             if (ep.res_f32) {
-                const float* rf = reinterpret_cast<const float*>(ep.res_hi) + off;
-                const float4 q0 = __ldg(reinterpret_cast<const float4*>(rf)), q1 = __ldg(reinterpret_cast<const float4*>(rf + 4));
-                rr[0] = q0.x; rr[1] = q0.y; rr[2] = q0.z; rr[3] = q0.w; rr[4] = q1.x; rr[5] = q1.y; rr[6] = q1.z; rr[7] = q1.w;
+                const float4 q = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.res_hi) + off));
+                rr[0] = q.x; rr[1] = q.y; rr[2] = q.z; rr[3] = q.w;
             } else {
-                load8(ep.res_hi + off, ep.res_lo ? ep.res_lo + off : nullptr, ep.lo_fp16, rr);
+                const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(ep.res_hi + off));
+                rr[0] = __uint_as_float(h2.x << 16); rr[1] = __uint_as_float(h2.x & 0xffff0000u);
+                rr[2] = __uint_as_float(h2.y << 16); rr[3] = __uint_as_float(h2.y & 0xffff0000u);
+                if (ep.res_lo != nullptr) {
+                    const uint2 l2 = __ldg(reinterpret_cast<const uint2*>(ep.res_lo + off));
+                    rr[0] += lo_to_f32((uint16_t)(l2.x & 0xffffu), ep.lo_fp16); rr[1] += lo_to_f32((uint16_t)(l2.x >> 16), ep.lo_fp16);
+                    rr[2] += lo_to_f32((uint16_t)(l2.y & 0xffffu), ep.lo_fp16); rr[3] += lo_to_f32((uint16_t)(l2.y >> 16), ep.lo_fp16);
+                }
             }
         }
         // the chain of rrv_epilogue, in the reference's operation order (rrv_common.cuh: apply_epilogue)
         if (ep.bias != nullptr) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] += bias[k];
+            for (int k = 0; k < V; ++k) v[k] += bias[k];
         }
         if (ep.act == 1) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.0f);
+            for (int k = 0; k < V; ++k) v[k] = fmaxf(v[k], 0.0f);
         } else if (ep.act == 2) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = v[k] > 0.0f ? v[k] : 0.2f * v[k];
+            for (int k = 0; k < V; ++k) v[k] = v[k] > 0.0f ? v[k] : 0.2f * v[k];
         }
         if (ep.norm1 != nullptr) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fminf(hi1[k], fmaxf(lo1[k], (v[k] - m1[k]) * r1[k]));
+            for (int k = 0; k < V; ++k) v[k] = fminf(hi1[k], fmaxf(lo1[k], (v[k] - m1[k]) * r1[k]));
         }
         if (ep.res_hi != nullptr) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] += rr[k];
+            for (int k = 0; k < V; ++k) v[k] += rr[k];
         }
         if (ep.norm2 != nullptr) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = fminf(hi2[k], fmaxf(lo2[k], (v[k] - m2[k]) * r2[k]));
+            for (int k = 0; k < V; ++k) v[k] = fminf(hi2[k], fmaxf(lo2[k], (v[k] - m2[k]) * r2[k]));
         }
         if (ep.affine != nullptr) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = v[k] * sc[k] + sh[k];
+            for (int k = 0; k < V; ++k) v[k] = v[k] * sc[k] + sh[k];
         }
         if (STATS) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < V; ++k) {
                 ssum[k] += v[k];
                 ssq[k] = fmaf(v[k], v[k], ssq[k]);
                 smn[k] = fminf(smn[k], v[k]);
@@ -152,22 +158,31 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const float* __restrict_
         }
         const long long o = (long long)p * C + c0;
         if (out_mode == RRV_OUT_PLANES) {
-            store8(out_hi + o, out_lo ? out_lo + o : nullptr, ep.lo_fp16, v);
+            uint32_t hw[2], lw[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                uint16_t h0, l0, h1, l1;
+                split_hi_lo(v[2 * k], ep.lo_fp16, h0, l0);
+                split_hi_lo(v[2 * k + 1], ep.lo_fp16, h1, l1);
+                hw[k] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                lw[k] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+            *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(hw[0], hw[1]);
+            if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(lw[0], lw[1]);
         } else {
             *reinterpret_cast<float4*>(out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(out_f32 + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
     }
     if (STATS) {
-        // threads t, t + C8, t + 2 C8, ... of the block own the same channel group (256 % C8 == 0)
-        __shared__ float s_red[4][256][8 + 1];
+        // threads t, t + CV, t + 2 CV, ... of the block own the same channel group (256 % CV == 0)
+        __shared__ float s_red[4][256][V + 1];
         const int t = threadIdx.x;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { s_red[0][t][k] = ssum[k]; s_red[1][t][k] = ssq[k]; s_red[2][t][k] = smn[k]; s_red[3][t][k] = smx[k]; }
+        for (int k = 0; k < V; ++k) { s_red[0][t][k] = ssum[k]; s_red[1][t][k] = ssq[k]; s_red[2][t][k] = smn[k]; s_red[3][t][k] = smx[k]; }
         __syncthreads();
-        const int groups = C8 < 256 ? C8 : 256;
-        for (int j = t; j < groups * 8; j += 256) {
-            const int g = j >> 3, k = j & 7;
+        const int groups = CV < 256 ? CV : 256;
+        for (int j = t; j < groups * V; j += 256) {
+            const int g = j / V, k = j % V;
             double sa = 0.0, sb = 0.0;
             float mn = CUDART_INF_F, mx = -CUDART_INF_F;
             for (int u = g; u < 256; u += groups) {
@@ -176,7 +191,7 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const float* __restrict_
                 mn = fminf(mn, s_red[2][u][k]);
                 mx = fmaxf(mx, s_red[3][u][k]);
             }
-            const int c = (int)((blockIdx.x * 256u + (unsigned)g) % (unsigned)C8) * 8 + k;      // the group thread g of this block owns
+            const int c = (int)((blockIdx.x * 256u + (unsigned)g) % (unsigned)CV) * V + k;      // the group thread g of this block owns
             atomicAdd(stats + C + c, sa);
             atomicAdd(stats + 2 * C + c, sb);
             if (stats_minmax) {
@@ -196,8 +211,8 @@ int pointwise(const float* in, long long in_bs, int N, int H, int W, int C, cons
     const long long total = (long long)N * H * W * (C / 8);
     if (total == 0) return 0;
     RRV_REQUIRE((long long)N * H * W < (1LL << 31), "rrv_pointwise: more than 2^31 pixels");
-    RRV_REQUIRE(C / 8 <= 256 && 256 % (C / 8) == 0, "rrv_pointwise: C / 8 must divide 256 (C=%d)", C);     // a thread keeps its channel group
-    const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 8);
+    RRV_REQUIRE(C / 4 <= 256 && 256 % (C / 4) == 0, "rrv_pointwise: C / 4 must divide 256 (C=%d)", C);     // a thread keeps its channel group
+    const int grid = (int)std::min<long long>((2 * total + 255) / 256, 148LL * 16);
     if (stats != nullptr) {
         pointwise_kernel<true><<<grid, 256, 0, st>>>(in, in_bs, N, H, W, C, make_epi(*ep, C), out_mode, (uint16_t*)out_hi,
                                                      (uint16_t*)out_lo, out_f32, stats, stats_minmax);

@@ -326,7 +326,7 @@ class StyleEngine:
         """pointwise pass + the finished partial statistics of what it wrote."""
         n_in, H, W, Cc = x_f32.shape
         n = kw.get("N") or n_in
-        if not self.fused_stats or 256 % (Cc // 8) != 0:
+        if not self.fused_stats:
             out = self._pointwise(x_f32, ep, to_f32=True, **kw)
             return out, self._stats_part(out)
         part = self._part_new(Cc, n * H * W)
@@ -789,6 +789,76 @@ class StyleEngine:
             N, H, W, _ = x.shape
         taps = self._vgg(top, x.contiguous(), kind, False, N, H, W, "style")
         return tuple(taps[i].permute(0, 3, 1, 2) for i in (0, 5, 10, 19))
+
+    # ------------------------------------------------------------------ backward of the frozen Vgg19 loss network
+    def _dgrad_weights(self, top):
+        """Data-gradient weights of the nine VGG convolutions: W'[ci][co][ky][kx] = W[co][ci][2-ky][2-kx] (channel axes swapped,
+        taps rotated by 180 degrees), packed once; the data gradient of a stride-1 'same' convolution is then rrv_conv2d itself."""
+        key = top + "/dgrad"
+        if key not in self.w:
+            convs = self.w[top]
+            flip = lambda w: w.transpose(0, 1).flip(2, 3).contiguous()
+            self.w[key] = [ConvW(flip(convs[0][0]), None)] + [ConvW(flip(cw._keep[:cw.Cout, :cw.Cin]), None) for cw in convs[1:]]
+        return self.w[key]
+
+    @torch.no_grad()
+    def vgg_features_train(self, x, top="Vgg19"):
+        """Vgg19.forward (train/style_networks.py:284-314) keeping what its backward needs: every ReLU output in fp32 NHWC.
+        Returns ((relu1_1, relu2_1, relu3_1, relu4_1) as NCHW views, saved)."""
+        if top not in self.w:
+            raise RuntimeError(f"no weights loaded under '{top}.*'")
+        N, _, H, W = x.shape
+        convs = self.w[top]
+        w0, b0 = convs[0]
+        cur = Planes(N, H, W, 64, self.x3, self.device)
+        y = torch.empty((N, H, W, 64), dtype=torch.float32, device=self.device)
+        L.check(self.lib.rrv_first_layer(x.contiguous().data_ptr(), 0, 0, N, H, W, w0.data_ptr(), b0.data_ptr(), L.ptr(cur.hi), L.ptr(cur.lo),
+                                         y.data_ptr(), L.stream()), "rrv_first_layer")
+        saved = [y]
+        ident = make_epilogue()
+        for (idx, _, _), cw in zip(VGG_CONVS[1:], convs[1:]):
+            y = self._conv(cw, cur, make_epilogue(bias=cw.bias, act=1), L.OUT_F32_NHWC)
+            saved.append(y)
+            if idx != 19:
+                cur = self._pointwise(y, ident)
+                if idx in VGG_POOL_AFTER:
+                    cur = self._pool(cur)
+        feats = tuple(saved[i].permute(0, 3, 1, 2) for i in (0, 2, 4, 8))
+        return feats, saved
+
+    @torch.no_grad()
+    def vgg_backward(self, saved, grads, top="Vgg19"):
+        """d(loss)/d(input image) of the frozen Vgg19 given d(loss)/d(relu1_1, relu2_1, relu3_1, relu4_1) (NCHW, any may be None):
+        per layer, ReLU backward fused with the split into operand planes (rrv_relu_backward), the data-gradient convolution on
+        the tensor cores, and rrv_maxpool2x2_backward where the forward pooled.  Returns fp32 NCHW [N, 3, H, W]."""
+        dw = self._dgrad_weights(top)
+        taps = {0: 0, 2: 1, 4: 2, 8: 3}                     # layer position -> feature index
+        pooled_after = {1, 3, 7}                            # conv1_2, conv2_2, conv3_4
+        g = None
+        for i in range(8, -1, -1):
+            y = saved[i]
+            N, H, W, Cc = y.shape
+            if i in pooled_after and g is not None:
+                gy = torch.empty_like(y)
+                L.check(self.lib.rrv_maxpool2x2_backward(g.data_ptr(), y.data_ptr(), N, H, W, Cc, gy.data_ptr(), L.stream()),
+                        "rrv_maxpool2x2_backward")
+                g = gy
+            gt = grads[taps[i]] if i in taps else None
+            if gt is not None:
+                gt = gt.permute(0, 2, 3, 1).contiguous().float()
+                if tuple(gt.shape) != tuple(y.shape):
+                    raise ValueError(f"gradient of feature {taps[i]} is {tuple(gt.shape)}, expected NCHW of {tuple(y.shape)}")
+            if g is None and gt is None:
+                continue
+            a, b = (g, gt) if g is not None else (gt, None)
+            gp = Planes(N, H, W, Cc, self.x3, self.device)
+            L.check(self.lib.rrv_relu_backward(a.data_ptr(), L.ptr(b), y.data_ptr(), y.numel(), L.ptr(gp.hi), L.ptr(gp.lo), L.stream()),
+                    "rrv_relu_backward")
+            if i == 0:
+                return self._conv(dw[0], gp, make_epilogue(), L.OUT_F32_NCHW, out_C=3)
+            g = self._conv(dw[i], gp, make_epilogue(), L.OUT_F32_NHWC)
+        N, H, W, _ = saved[0].shape
+        return torch.zeros((N, 3, H, W), dtype=torch.float32, device=self.device)
 
     @torch.no_grad()
     def feature_mean_std(self, feat_nchw_view):

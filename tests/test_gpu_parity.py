@@ -172,12 +172,14 @@ def test_conv_bf16_mode(L, dev):
     assert rel_linf(got, ref.bfloat16().float()) < 2.0 ** -7
 
 
-def test_conv_full_epilogue_chain(L, dev):
-    """bias -> LeakyReLU -> saved-stat norm -> + half-res residual -> saved-stat norm -> AdaIN."""
+@pytest.mark.parametrize("size", [(2, 16, 24), (2, 38, 70), (1, 52, 126), (3, 8, 16)])
+def test_conv_full_epilogue_chain(L, dev, size):
+    """bias -> LeakyReLU -> saved-stat norm -> + half-res residual -> saved-stat norm -> AdaIN (ResidualBlock.conv2 of slice2:
+    merged-tap main loop, residual tile by TMA, output through the staging rows and TMA stores; ragged tile edges, batches)."""
     from rerevst_code_b200.engine import ConvW, make_epilogue
     from oracle import stylenet
     g = torch.Generator().manual_seed(11)
-    N, H, W, Cc = 2, 16, 24, 64
+    (N, H, W), Cc = size, 64
     x = torch.randn(N, Cc, H, W, generator=g)
     w = torch.randn(Cc, Cc, 3, 3, generator=g) / 24.0
     b = torch.randn(Cc, generator=g) * 0.1
@@ -947,7 +949,7 @@ def test_conv_fused_statistics(L, dev, case):
         L.check(L.lib().rrv_conv2d(C.byref(d), L.IMPL_TCGEN05, L.stream()))
         # same arithmetic; the nearest-x2 layer with Cout <= 64 takes the merged-phase main loop when statistics are requested
         # (partial sums meet in the epilogue instead of in TMEM: last-bit differences)
-        assert torch.equal(out, plain) or (ups and Cout <= 64 and torch.allclose(out, plain, rtol=1e-5, atol=1e-6))
+        assert torch.equal(out, plain) or (ups and Cout <= 64 and torch.allclose(out, plain, rtol=1e-4, atol=1e-5 * float(plain.abs().max())))
         ref = torch.empty((5, Cout), dtype=torch.float64, device=dev)
         L.check(L.lib().rrv_channel_stats(out.data_ptr(), N * H * W, Cout, ref.data_ptr(), L.stream()))
         part, ref = part.cpu(), ref.cpu()
@@ -1009,3 +1011,80 @@ def test_fold_filter_kernel_matches_host_fold(L, dev, state_dict):
     u_a = eng._conv(up, t_b, make_epilogue(bias=up.bias), L.OUT_F32_NHWC)
     u_b = eng._conv(up_ref, t_b, make_epilogue(bias=up_ref.bias), L.OUT_F32_NHWC)
     assert rel_linf(u_a.cpu(), u_b.cpu()) < 2e-5
+
+
+def _vgg_backward_reference(saved, cots, sd):
+    """The chain rule through Vgg19 in float64 on the CPU, using the ReLU outputs the GPU forward saved (so that units whose
+    pre-activation is within rounding of zero take the same side in both computations)."""
+    from oracle import stylenet
+    names = stylenet._enc_names("Vgg19")
+    taps, pooled_after, g = {0: 0, 2: 1, 4: 2, 8: 3}, {1, 3, 7}, None
+    for i in range(8, -1, -1):
+        y = saved[i].permute(0, 3, 1, 2).double().cpu()
+        if i in pooled_after and g is not None:
+            _, idx = F.max_pool2d(y, 2, 2, return_indices=True)
+            g = F.max_unpool2d(g, idx, 2, 2, output_size=y.shape[-2:])
+        if i in taps and cots[taps[i]] is not None:
+            g = cots[taps[i]].double() if g is None else g + cots[taps[i]].double()
+        if g is None:
+            continue
+        g = g * (y > 0)
+        g = F.conv_transpose2d(g, sd[names[i][0]].double(), padding=1)
+    return g
+
+
+def test_vgg19_loss_network_backward(L, dev, state_dict):
+    """train.py:376-414: Loss.backward() runs first through the frozen Vgg19 (train/style_networks.py:284-314).  Its data gradient
+    here = ReLU / max-pool backward kernels + the tensor-core convolution on transposed, rotated weights; checked against
+    torch.autograd through the CPU oracle's Vgg19, for a weighted sum of the four features and for content + style loss."""
+    from oracle import stylenet
+    from rerevst_code_b200.style_networks import TransformerNet
+    net = TransformerNet().to(dev)
+    net.load_state_dict(state_dict)
+    sd = {k: v.float() for k, v in state_dict.items()}
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 3, 44, 60, generator=g)                     # 44 -> 22 -> 11 -> 5: an odd size before the last pool
+    cot = [torch.randn(s, generator=g) for s in ((2, 64, 44, 60), (2, 128, 22, 30), (2, 256, 11, 15), (2, 512, 5, 7))]
+    xr = x.clone().requires_grad_(True)
+    ref_feats = stylenet.vgg19_features(xr, sd, top="Vgg19")
+    sum((f * c).sum() for f, c in zip(ref_feats, cot)).backward()
+    xd = x.to(dev).requires_grad_(True)
+    feats = net.vgg19(xd)
+    for f, r in zip(feats, ref_feats):
+        assert rel_linf(f.detach().cpu().numpy(), r.detach().numpy()) < TOL
+    sum((f * c.to(dev)).sum() for f, c in zip(feats, cot)).backward()
+    # (a) the kernels, exactly: the same chain rule in float64 on the CPU with the GPU forward's ReLU outputs
+    saved = net._eng().vgg_features_train(x.to(dev), "Vgg19")[1]
+    exact = _vgg_backward_reference(saved, cot, sd)
+    assert rel_linf(xd.grad.cpu().numpy(), exact.numpy()) < 2e-4
+    # (b) torch.autograd through the CPU oracle.  A ReLU unit whose pre-activation is within rounding of zero may take the other
+    # side there (a handful among ~10^6); each such unit changes the gradient over its receptive field by a few percent, so the
+    # comparison is on the relative L2 error and on the bulk of the elements rather than on the maximum
+    def close(a, b):
+        a, b = a.double(), b.double()
+        return float((a - b).norm() / b.norm()) < 2e-2 and float(((a - b).abs() < 2e-3 * b.abs().max()).double().mean()) > 0.9
+    assert close(xd.grad.cpu(), xr.grad)
+    # only the deepest feature carries a gradient (content loss): the shallower taps contribute nothing
+    xd2 = x.to(dev).requires_grad_(True)
+    (net.vgg19(xd2).relu4_1 * cot[3].to(dev)).sum().backward()
+    assert rel_linf(xd2.grad.cpu().numpy(), _vgg_backward_reference(saved, [None, None, None, cot[3]], sd).numpy()) < 2e-4
+    # content + style loss of a "styled" frame against fixed targets, as in train.py:392-399
+    target = torch.randn(2, 3, 44, 60, generator=g)
+    with torch.no_grad():
+        ft = net.vgg19(target.to(dev))
+    xd3 = x.to(dev).requires_grad_(True)
+    fx = net.vgg19(xd3)
+    loss = net.content_loss(fx, ft) + 10.0 * net.style_loss(fx, ft)
+    loss.backward()
+
+    def ref_loss(xx):
+        fa = stylenet.vgg19_features(xx, sd, top="Vgg19")
+        fb = [t.detach() for t in stylenet.vgg19_features(target, sd, top="Vgg19")]
+        ms = lambda f: (f.mean((2, 3)), (f.var((2, 3)) + 1e-5).sqrt())
+        sl = sum(F.mse_loss(ms(a)[0], ms(b)[0]) + F.mse_loss(ms(a)[1], ms(b)[1]) for a, b in zip(fa, fb))
+        return F.mse_loss(fa[3], fb[3]) + 10.0 * sl
+    xr3 = x.clone().requires_grad_(True)
+    lr = ref_loss(xr3)
+    lr.backward()
+    assert abs(float(loss) - float(lr)) < 2e-3 * abs(float(lr))
+    assert close(xd3.grad.cpu(), xr3.grad)
