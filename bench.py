@@ -423,6 +423,9 @@ def main():
     # ---- per-clip pre-pass (not part of the timed per-frame loop; reported separately) ----
     n_samples = max(args.samples, world) if world > 1 else args.samples
     sample_frames = [synthetic_frame(h, w, 50 + i) for i in range(n_samples)]      # host-side synthesis is not pre-pass time
+    if world > 1:          # NCCL communicator set-up (first collective) is not pre-pass time either
+        from rerevst_code_b200.dist import allgather_parts
+        allgather_parts(torch.zeros((5, 64), dtype=torch.float64, device=dev))
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     fw.clean()

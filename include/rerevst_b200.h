@@ -210,7 +210,8 @@ int rrv_stats_merge(const double* parts, int nparts, int C, double* merged, void
  *         (EncoderStyle.cal_mean_std :304-315, unbiased variance, eps 1e-5);
  * kind 2: float[C] = mean (FilterPredictor spatial/batch mean :163-167);
  * kind 3: float[4][C] = {mean, rstd, -inf, +inf}: frame-mode InstanceNorm (no clamp,
- *         style_network_frame.py:39-43). */
+ *         style_network_frame.py:39-43).
+ * kind | 16: row 2 of `part` still holds sum(x^2) (straight from a one-pass producer, no rrv_stats_sums_to_m2 in between). */
 int rrv_stats_finalize(const double* part, int C, int kind, float eps, float* out, void* stream);
 /* FilterPredictor FC (:157,169): out[1024] = W[1024][64] . concat(c[32], s[32]) + b. */
 int rrv_filter_fc(const float* w, const float* b, const float* c_mean, const float* s_mean,

@@ -555,7 +555,7 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
         }
     }
     if (MODE == 0) ptx::tmem_ld32_wait(r);
-    if (ST || (FLAGS == 0 && stage != 0u)) {       // warp-uniform: before any lane leaves
+    if (ST || ((FLAGS == 0 || STATS) && stage != 0u)) {       // warp-uniform: before any lane leaves
         if ((threadIdx.x & 31) == 0) ptx::bulk_wait_read0();
         __syncwarp();
     }
@@ -609,6 +609,17 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
 #pragma unroll
             for (int k = 0; k < 8; ++k) xs[g * 8 + k] = x[k];
             if (!px.valid) continue;
+            if (stage != 0u) {
+                // fp32 NHWC through the staging rows (frame mode / pre-pass): rows of 128 bytes = the chunk's 32 fp32 channels of one
+                // pixel, SWIZZLE_128B (16-byte piece ^= address bits 7..9); row = lane (MODE 1) or lane - 1 (MODE 2)
+                const int row = (int)(threadIdx.x & 31) - (MODE == 2 ? 1 : 0);
+                const uint32_t base = stage + (uint32_t)(row * 128), key = (uint32_t)(row & 7);
+                ptx::sts_v4(base + ((((uint32_t)(2 * g)) ^ key) << 4),
+                            make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3])));
+                ptx::sts_v4(base + ((((uint32_t)(2 * g + 1)) ^ key) << 4),
+                            make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7])));
+                continue;
+            }
         }
         store_group<(FLAGS < 0)>(o, x, px, c0, c0 + 8 <= o.Cout ? 8 : o.Cout - c0);
     }
@@ -1275,7 +1286,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     if ((J) < p.Cout_pad / CW) {                                                                                                       \
         float xs[CW];                                                                                                                  \
         epilogue_chunk<FLAGS, 2>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)((J) * CW), px, (J) * CW, (J) * CW, p.Cout_pad, false, nullptr, \
-                                 nullptr, half, xs);                                                                                   \
+                                 nullptr, half, xs, o_stage);                                                                          \
+        if (p.ostage) {                                                                                                                \
+            ptx::fence_proxy_async();                                                                                                  \
+            __syncwarp();                                                                                                              \
+            if (lane == 0 && iy < p.in_H) {                                                                                            \
+                ptx::tma_store_5d(&map_o_hi, o_stage, (J) * CW, half, x0, 2 * iy + ph, n);                                             \
+                ptx::bulk_commit();                                                                                                    \
+            }                                                                                                                          \
+        }                                                                                                                              \
         stat_add<(J)>(sacc, xs, valid, lane, st_mm);                                                                                   \
     }
                     RRV_STAT_CHUNK2(0) RRV_STAT_CHUNK2(1)
@@ -1404,7 +1423,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const int ch = half + 2 * (J);                                                                                                 \
         float xs[CW];                                                                                                                  \
         epilogue_chunk<FLAGS, DXM ? 1 : 0>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, ch * CW, p.BNe, false, \
-                                           nullptr, nullptr, 0, xs);                                                                   \
+                                           nullptr, nullptr, 0, xs, DXM ? o_stage : 0u);                                               \
+        if (DXM && p.ostage) {     /* merged taps, Cout_pad <= 64: this warp's only chunk; its row of 30 pixels x 32 fp32 channels */ \
+            ptx::fence_proxy_async();                                                                                                  \
+            __syncwarp();                                                                                                              \
+            if (lane == 0 && iy < p.in_H) {                                                                                            \
+                ptx::tma_store_4d(&map_o_hi, o_stage, ch * CW, x0, iy, n);                                                             \
+                ptx::bulk_commit();                                                                                                    \
+            }                                                                                                                          \
+        }                                                                                                                              \
         stat_add<(J)>(sacc, xs, valid, lane, st_mm);                                                                                   \
     }
                     RRV_STAT_CHUNK(0) RRV_STAT_CHUNK(1) RRV_STAT_CHUNK(2) RRV_STAT_CHUNK(3)
@@ -1554,24 +1581,26 @@ int encode_w_map(CUtensorMap* m, const void* base, int rows, int Cin, int BN) {
 //   mode 1: box = 32 channels x 30 pixels of one row, rows of 64 bytes, SWIZZLE_64B (one epilogue warp's share of a tile row);
 //   mode 2: the tensor seen as (C, column parity, W / 2, H, N): box = 32 channels x 1 parity x 30 low-res columns, SWIZZLE_64B
 //           (one 32-channel chunk of one column phase of one output row of the nearest-x2 convolution).
-int encode_out_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int mode) {
+// f32: the same boxes over an fp32 NHWC tensor (rows of 128 bytes, SWIZZLE_128B): the statistics-collecting instantiations.
+int encode_out_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int mode, bool f32 = false) {
     CUresult r;
+    const cuuint64_t eb = f32 ? 4 : 2;
+    const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapSwizzle sw = f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     if (mode == 1) {
         const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-        const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        const cuuint64_t strides[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
         const cuuint32_t box[4] = {32, 30, 1, 1};
         const cuuint32_t es[4] = {1, 1, 1, 1};
-        r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        r = encode_fn()(m, dt, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         const cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)(W / 2), (cuuint64_t)H, (cuuint64_t)N};
-        const cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)C * 4, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+        const cuuint64_t strides[4] = {(cuuint64_t)C * eb, (cuuint64_t)C * 2 * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
         const cuuint32_t box[5] = {32, 1, 30, 1, 1};
         const cuuint32_t es[5] = {1, 1, 1, 1, 1};
-        r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        r = encode_fn()(m, dt, 5, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                        CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(output %dx%dx%dx%d, mode %d) failed: %d", N, H, W, C, mode, (int)r);
@@ -1712,6 +1741,10 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         if (d.dxm == 1 && p->Cout % CW == 0 && (fl == 0 || fl == (EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF))) d.ostage = 2048;
         if (d.dxm == 2 && p->Cout == 64 && fl == EPI_N1) d.ostage = 2048;
     }
+    // the statistics-collecting instantiations write fp32 NHWC: the same staging, one 4 KB buffer of 128-byte rows per warp
+    const bool ostage_f32 = !no_ostage && d.dxm && p->out_mode == RRV_OUT_F32_NHWC && p->stats != nullptr && !p->pool && p->Cout == d.Cout_pad &&
+                            ((d.dxm == 1 && p->Cout % CW == 0) || (d.dxm == 2 && p->Cout == 64));
+    if (ostage_f32) d.ostage = 2048;
     if (d.ostage) {      // the staging rows must leave room for two A stages and two weight slots (CTA pairs halve the weight slots)
         const bool pair_ok = g_tune.pair && num_sms() % 2 == 0;
         const int bn = (d.dxm == 2 ? 4 : 3) * d.Cout_pad;
@@ -1914,7 +1947,10 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     d.ostage_off = (d.a_stages * a_stage + d.b_slots * b_slot + d.Cout_pad * TAB_BYTES + xchg_bytes + 1023) / 1024 * 1024;
     memset(&t_mo_hi, 0, sizeof(t_mo_hi));
     memset(&t_mo_lo, 0, sizeof(t_mo_lo));
-    if (d.ostage) {
+    if (d.ostage && ostage_f32) {
+        if (encode_out_map(&t_mo_hi, p->out_f32, d.N, d.o.H, d.o.W, p->Cout, d.dxm, true)) return 1;
+        t_mo_lo = t_mo_hi;
+    } else if (d.ostage) {
         if (encode_out_map(&t_mo_hi, p->out_hi, d.N, d.o.H, d.o.W, p->Cout, d.dxm)) return 1;
         if (p->out_lo) {
             if (encode_out_map(&t_mo_lo, p->out_lo, d.N, d.o.H, d.o.W, p->Cout, d.dxm)) return 1;

@@ -65,7 +65,7 @@ int maxpool2x2(const void* in_hi, const void* in_lo, int N, int H, int W, int C,
 // STATS: the per-channel {sum, sum of squares[, min, max]} of the values written also go to `stats` (double[5][C]): fp32 per thread
 // (a few dozen pixels), then double across the block's threads of equal group through shared memory, one atomic per channel.
 template <bool STATS>
-__global__ void __launch_bounds__(256) pointwise_kernel(const float* __restrict__ in, long long in_bs, int N, int H, int W,
+__global__ void __launch_bounds__(256, 2) pointwise_kernel(const float* __restrict__ in, long long in_bs, int N, int H, int W,
                                                         int C, EpiDev ep, int out_mode, uint16_t* out_hi,
                                                         uint16_t* out_lo, float* out_f32, double* stats, int stats_minmax) {
     constexpr int V = 4;                      // channels per thread: 16-byte loads, and the constants below fit ~90 registers
@@ -96,81 +96,103 @@ __global__ void __launch_bounds__(256) pointwise_kernel(const float* __restrict_
         sc[k] = ep.affine ? __ldg(ep.affine + c) : 1.0f;
         sh[k] = ep.affine ? __ldg(ep.affine + C + c) : 0.0f;
     }
-    for (unsigned p = gtid / (unsigned)CV; p < npix; p += pstride) {
-        unsigned n = 0, rem = p;
-        if (N > 1) { n = p / HW; rem = p - n * HW; }
-        const float4 a = __ldg(reinterpret_cast<const float4*>(in + (long long)n * in_bs + (long long)rem * C + c0));
-        float v[V] = {a.x, a.y, a.z, a.w};
-        float rr[V];
-        if (ep.res_hi != nullptr) {
-            const unsigned y = rem / (unsigned)W, x = rem - y * (unsigned)W;
-            const long long off = (long long)n * ep.res_batch_stride + ((long long)(y >> ep.res_shift) * ep.res_W + (x >> ep.res_shift)) * C + c0;
-            if (ep.res_f32) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.res_hi) + off));
-                rr[0] = q.x; rr[1] = q.y; rr[2] = q.z; rr[3] = q.w;
-            } else {
-                const uint2 h2 = __ldg(reinterpret_cast<const uint2*>(ep.res_hi + off));
-                rr[0] = __uint_as_float(h2.x << 16); rr[1] = __uint_as_float(h2.x & 0xffff0000u);
-                rr[2] = __uint_as_float(h2.y << 16); rr[3] = __uint_as_float(h2.y & 0xffff0000u);
-                if (ep.res_lo != nullptr) {
-                    const uint2 l2 = __ldg(reinterpret_cast<const uint2*>(ep.res_lo + off));
-                    rr[0] += lo_to_f32((uint16_t)(l2.x & 0xffffu), ep.lo_fp16); rr[1] += lo_to_f32((uint16_t)(l2.x >> 16), ep.lo_fp16);
-                    rr[2] += lo_to_f32((uint16_t)(l2.y & 0xffffu), ep.lo_fp16); rr[3] += lo_to_f32((uint16_t)(l2.y >> 16), ep.lo_fp16);
+    // U pixels per trip: all their loads are issued before the first value is used (one 16-byte load per pixel and tensor would
+    // leave too few bytes in flight per SM for an HBM-bound pass)
+    constexpr int U = 4;
+    for (unsigned p0 = gtid / (unsigned)CV; p0 < npix; p0 += U * pstride) {
+        float4 a[U], q[U];
+        uint2 qh[U], ql[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned p = p0 + (unsigned)u * pstride;
+            ok[u] = p < npix;
+            if (!ok[u]) continue;
+            unsigned n = 0, rem = p;
+            if (N > 1) { n = p / HW; rem = p - n * HW; }
+            a[u] = __ldg(reinterpret_cast<const float4*>(in + (long long)n * in_bs + (long long)rem * C + c0));
+            if (ep.res_hi != nullptr) {
+                const unsigned y = rem / (unsigned)W, x = rem - y * (unsigned)W;
+                const long long off = (long long)n * ep.res_batch_stride + ((long long)(y >> ep.res_shift) * ep.res_W + (x >> ep.res_shift)) * C + c0;
+                if (ep.res_f32) {
+                    q[u] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ep.res_hi) + off));
+                } else {
+                    qh[u] = __ldg(reinterpret_cast<const uint2*>(ep.res_hi + off));
+                    if (ep.res_lo != nullptr) ql[u] = __ldg(reinterpret_cast<const uint2*>(ep.res_lo + off));
                 }
             }
         }
-        // the chain of rrv_epilogue, in the reference's operation order (rrv_common.cuh: apply_epilogue)
-        if (ep.bias != nullptr) {
 #pragma unroll
-            for (int k = 0; k < V; ++k) v[k] += bias[k];
-        }
-        if (ep.act == 1) {
-#pragma unroll
-            for (int k = 0; k < V; ++k) v[k] = fmaxf(v[k], 0.0f);
-        } else if (ep.act == 2) {
-#pragma unroll
-            for (int k = 0; k < V; ++k) v[k] = v[k] > 0.0f ? v[k] : 0.2f * v[k];
-        }
-        if (ep.norm1 != nullptr) {
-#pragma unroll
-            for (int k = 0; k < V; ++k) v[k] = fminf(hi1[k], fmaxf(lo1[k], (v[k] - m1[k]) * r1[k]));
-        }
-        if (ep.res_hi != nullptr) {
-#pragma unroll
-            for (int k = 0; k < V; ++k) v[k] += rr[k];
-        }
-        if (ep.norm2 != nullptr) {
-#pragma unroll
-            for (int k = 0; k < V; ++k) v[k] = fminf(hi2[k], fmaxf(lo2[k], (v[k] - m2[k]) * r2[k]));
-        }
-        if (ep.affine != nullptr) {
-#pragma unroll
-            for (int k = 0; k < V; ++k) v[k] = v[k] * sc[k] + sh[k];
-        }
-        if (STATS) {
-#pragma unroll
-            for (int k = 0; k < V; ++k) {
-                ssum[k] += v[k];
-                ssq[k] = fmaf(v[k], v[k], ssq[k]);
-                smn[k] = fminf(smn[k], v[k]);
-                smx[k] = fmaxf(smx[k], v[k]);
+        for (int u = 0; u < U; ++u) {
+            if (!ok[u]) continue;
+            const unsigned p = p0 + (unsigned)u * pstride;
+            float v[V] = {a[u].x, a[u].y, a[u].z, a[u].w};
+            float rr[V];
+            if (ep.res_hi != nullptr) {
+                if (ep.res_f32) {
+                    rr[0] = q[u].x; rr[1] = q[u].y; rr[2] = q[u].z; rr[3] = q[u].w;
+                } else {
+                    rr[0] = __uint_as_float(qh[u].x << 16); rr[1] = __uint_as_float(qh[u].x & 0xffff0000u);
+                    rr[2] = __uint_as_float(qh[u].y << 16); rr[3] = __uint_as_float(qh[u].y & 0xffff0000u);
+                    if (ep.res_lo != nullptr) {
+                        rr[0] += lo_to_f32((uint16_t)(ql[u].x & 0xffffu), ep.lo_fp16); rr[1] += lo_to_f32((uint16_t)(ql[u].x >> 16), ep.lo_fp16);
+                        rr[2] += lo_to_f32((uint16_t)(ql[u].y & 0xffffu), ep.lo_fp16); rr[3] += lo_to_f32((uint16_t)(ql[u].y >> 16), ep.lo_fp16);
+                    }
+                }
             }
-        }
-        const long long o = (long long)p * C + c0;
-        if (out_mode == RRV_OUT_PLANES) {
-            uint32_t hw[2], lw[2];
+            // the chain of rrv_epilogue, in the reference's operation order (rrv_common.cuh: apply_epilogue)
+            if (ep.bias != nullptr) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                uint16_t h0, l0, h1, l1;
-                split_hi_lo(v[2 * k], ep.lo_fp16, h0, l0);
-                split_hi_lo(v[2 * k + 1], ep.lo_fp16, h1, l1);
-                hw[k] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                lw[k] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                for (int k = 0; k < V; ++k) v[k] += bias[k];
             }
-            *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(hw[0], hw[1]);
-            if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(lw[0], lw[1]);
-        } else {
-            *reinterpret_cast<float4*>(out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+            if (ep.act == 1) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) v[k] = fmaxf(v[k], 0.0f);
+            } else if (ep.act == 2) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) v[k] = v[k] > 0.0f ? v[k] : 0.2f * v[k];
+            }
+            if (ep.norm1 != nullptr) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) v[k] = fminf(hi1[k], fmaxf(lo1[k], (v[k] - m1[k]) * r1[k]));
+            }
+            if (ep.res_hi != nullptr) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) v[k] += rr[k];
+            }
+            if (ep.norm2 != nullptr) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) v[k] = fminf(hi2[k], fmaxf(lo2[k], (v[k] - m2[k]) * r2[k]));
+            }
+            if (ep.affine != nullptr) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) v[k] = v[k] * sc[k] + sh[k];
+            }
+            if (STATS) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    ssum[k] += v[k];
+                    ssq[k] = fmaf(v[k], v[k], ssq[k]);
+                    smn[k] = fminf(smn[k], v[k]);
+                    smx[k] = fmaxf(smx[k], v[k]);
+                }
+            }
+            const long long o = (long long)p * C + c0;
+            if (out_mode == RRV_OUT_PLANES) {
+                uint32_t hw[2], lw[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    uint16_t h0, l0, h1, l1;
+                    split_hi_lo(v[2 * k], ep.lo_fp16, h0, l0);
+                    split_hi_lo(v[2 * k + 1], ep.lo_fp16, h1, l1);
+                    hw[k] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                    lw[k] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                }
+                *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(hw[0], hw[1]);
+                if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(lw[0], lw[1]);
+            } else {
+                *reinterpret_cast<float4*>(out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+            }
         }
     }
     if (STATS) {

@@ -137,22 +137,28 @@ int stats_merge(const double* parts, int nparts, int C, double* merged, cudaStre
     return check_launch("stats_merge_kernel");
 }
 
-__global__ void stats_finalize_kernel(const double* __restrict__ part, int C, int kind, float eps, float* __restrict__ out) {
+// from_sums: row 2 of the partial still holds sum(x^2) (a one-pass producer, see rrv_stats_sums_to_m2): M2 is formed here.
+__global__ void stats_finalize_kernel(const double* __restrict__ part, int C, int kind, float eps, float* __restrict__ out, int from_sums) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double n = part[c];
     const float mean = (float)(part[C + c] / n);
+    double m2 = part[2 * C + c];
+    if (from_sums) {
+        m2 -= part[C + c] * part[C + c] / n;
+        m2 = m2 > 0.0 ? m2 : 0.0;
+    }
     if (kind == 2) { out[c] = mean; return; }
     if (kind == 1) {
         // EncoderStyle.cal_mean_std: sqrt(var_unbiased + eps), mean  -> AdaIN {scale, shift}
-        const float var = (float)(part[2 * C + c] / (n > 1.0 ? n - 1.0 : 1.0));
+        const float var = (float)(m2 / (n > 1.0 ? n - 1.0 : 1.0));
         out[c] = sqrtf(var + eps);
         out[C + c] = mean;
         return;
     }
     // InstanceNorm.compute: rsqrt(mean((x-mean)^2) + eps); x_min / x_max of the normalised tensor.
     // fp32 subtraction and multiplication are monotone, so max((x-m)*r) == (max(x)-m)*r bit for bit.
-    const float var = (float)(part[2 * C + c] / n);
+    const float var = (float)(m2 / n);
     const float rstd = 1.0f / sqrtf(var + eps);
     out[c] = mean;
     out[C + c] = rstd;
@@ -167,8 +173,10 @@ __global__ void stats_finalize_kernel(const double* __restrict__ part, int C, in
 
 int stats_finalize(const double* part, int C, int kind, float eps, float* out, cudaStream_t st) {
     RRV_REQUIRE(part && out, "rrv_stats_finalize: NULL tensor");
+    const int from_sums = (kind & 16) ? 1 : 0;
+    kind &= 15;
     RRV_REQUIRE(kind >= 0 && kind <= 3, "rrv_stats_finalize: bad kind %d", kind);
-    stats_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(part, C, kind, eps, out);
+    stats_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(part, C, kind, eps, out, from_sums);
     return check_launch("stats_finalize_kernel");
 }
 

@@ -147,6 +147,7 @@ class StyleEngine:
         self.q1_sample = None        # Encoder output of the clip's first sampled frame when it lives on another rank (dist.py)
         self.stats_allgather = None  # set by dist.ShardedPrepass: part[5,C] -> parts[G,5,C]
         self._plans = OrderedDict()
+        self._sums = set()           # data pointers of one-pass partials whose row 2 still holds sum(x^2) (see _part_done)
         self.profile = None          # list -> (label, start_event, end_event, flops) per conv launch (bench.py)
         self.graph_launches = 0      # kernels launched through CUDA-graph replays (not seen by rrv_launch_count)
 
@@ -297,7 +298,11 @@ class StyleEngine:
         return part
 
     def _part_done(self, part):
-        """{n, sum, sum of squares, min, max} -> {n, sum, M2, min, max}, merged over the ranks of a sharded pre-pass."""
+        """{n, sum, sum of squares, min, max} -> {n, sum, M2, min, max}, merged over the ranks of a sharded pre-pass.  In one
+        process the conversion is left to rrv_stats_finalize (kind | 16): one small launch less per statistic point."""
+        if self.stats_allgather is None:
+            self._sums.add(part.data_ptr())
+            return part
         Cc = part.shape[1]
         L.check(self.lib.rrv_stats_sums_to_m2(part.data_ptr(), Cc, L.stream()), "rrv_stats_sums_to_m2")
         return self._merge_ranks(part)
@@ -350,6 +355,9 @@ class StyleEngine:
         Cc = part.shape[1]
         rows = {0: 4, 1: 2, 2: 1, 3: 4}[kind]
         out = torch.empty((rows, Cc), dtype=torch.float32, device=self.device)
+        if part.data_ptr() in self._sums:              # a one-pass partial: row 2 is still the sum of squares
+            self._sums.discard(part.data_ptr())
+            kind |= 16
         L.check(self.lib.rrv_stats_finalize(part.data_ptr(), Cc, kind, eps, out.data_ptr(), L.stream()), "rrv_stats_finalize")
         return out
 

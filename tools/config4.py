@@ -119,7 +119,7 @@ def main():
         dist.all_gather(all_d, digest)
         same = all(torch.equal(all_d[0], d) for d in all_d)
     if rank == 0:
-        print(json.dumps({
+        print(file=bench._JSON_OUT, flush=True, *[json.dumps({
             "config": f"{args.frames}-frame {args.size} clip padded to {ph}x{pw}, {len(idx)} sampled frames ({h}x{w}, unpadded) sharded over "
                       f"{world} rank(s): {hi - lo} per rank, strong scaling ({n_local} frames per rank)",
             "n_gpus": world, "prepass_s_max_over_ranks": pre_s, "prepass_peak_device_memory_gb_max_over_ranks": peak_gb,
@@ -127,7 +127,7 @@ def main():
             "clip_loop_device_frames_per_s": args.frames / (ms_dev * 1e-3), "clip_loop_device_s": ms_dev * 1e-3,
             "clip_loop_e2e_frames_per_s": args.frames / (ms_e2e * 1e-3), "clip_loop_e2e_s": ms_e2e * 1e-3,
             "e2e": "host uint8 frames in, host uint8 BGR frames out (transfer_stream, out_dtype='u8')",
-            "whole_job_s": pre_s + ms_e2e * 1e-3}))
+            "whole_job_s": pre_s + ms_e2e * 1e-3})])
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

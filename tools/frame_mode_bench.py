@@ -18,13 +18,13 @@ fw.prepare_style(bench.synthetic_frame(512, 512, 1))
 eng = fw.model._eng()
 frames = [torch.from_numpy(bench.reflect_pad(bench.synthetic_frame(h, w, 100 + i), ph, pw)).unsqueeze(0).cuda() for i in range(2)]
 for i in range(3):
-    eng.forward_frame(frames[i % 2], kind=1)
+    eng.forward_frame_graphed(frames[i % 2], kind=1)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-steps = 20
+steps = 40
 e0.record()
 for i in range(steps):
-    eng.forward_frame(frames[i % 2], kind=1)
+    eng.forward_frame_graphed(frames[i % 2], kind=1)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
