@@ -322,8 +322,8 @@ def run_config5(sd, dev):
             "vgg19_tflops_algorithmic": 2 * B * 126.53e9 / (ms_vgg * 1e-3) / 1e12, "validation_one_frame_ms": ms_val,
             "parity": {"warp_indices_exact": exact, "warped_bit_equal": bool(np.array_equal(warped.cpu().numpy(), ref_w)),
                        "loss_rel_err": abs(float(loss) - ref_loss) / ref_loss, "loss_tolerance": 1e-6},
-            "note": "BASELINE.json configs[4]: B=4, 512x512; per-call times include the Python + ctypes launch path (8.4 MB per warp call: "
-                    "launch-latency bound; kernel-only times are in profiles/)"}
+            "note": "BASELINE.json configs[4]: B=4, 512x512; per-call times include the Python + ctypes launch path (33.5 MB per warp call: "
+                    "launch-latency bound at this size; kernel-only times are in profiles/r2_warp_kernels.csv)"}
 
 
 def run_frame_mode(sd, dev, precision, kernels, pk, check):
