@@ -113,17 +113,14 @@ int rrv_conv2d(const rrv_conv* p, int impl, void* stream);
  * w_oihw: fp32 [Cout][Cin][k][k] (PyTorch layout) on the device. */
 int64_t rrv_tc_weight_bytes(int Cin, int Cout, int ksize, int ups);
 int rrv_pack_weights_tc(const float* w_oihw, int Cin, int Cout, int ksize, int ups, void* blob, void* stream);
-/* Tuning knobs of the tensor-core kernel (defaults 256, 16, 6): widest Cout tile, width of the
- * 128-pixel spatial tile (8..128, power of two), deepest shared-memory pipeline. */
-int rrv_tc_tune(int max_bn, int tile_w, int max_stages);
-/* Main-loop variant (default 2, 2, 0): version 1 = one TMA box per tap; 2 = one box per (chunk, dx) shared by
- * the three dy taps, `mt` (1|2) 128-pixel M tiles per weight tile, resident weights when they all fit.
- * ups_v1 != 0 sends the nearest-x2 convolutions through the version-1 main loop. */
-int rrv_tc_tune2(int version, int mt, int ups_v1);
+/* Tuning knobs of the tensor-core kernel, for kernel development and the variant tests (process-global, not thread-safe: set
+ * them before any other thread launches convolutions).  Defaults 256, 2: widest Cout tile; 128-pixel M tiles per weight tile
+ * in the row-reuse main loop (1 | 2). */
+int rrv_tc_tune(int max_bn, int mt);
 /* CTA pairs (tcgen05 cta_group::2, clusters of 2): enabled by default for Cout tiles >= min_bn (64). */
 int rrv_tc_tune_pair(int enable, int min_bn);
-/* Merge the three dy taps of a 3x3 convolution into one MMA along N (N = 3 Cout) when 3 Cout <= 256: the
- * 64-channel layers, whose cost is the A-operand fetch.  Enabled by default. */
+/* Merge the three dx taps of a 3x3 convolution (and the column phases of a nearest-x2 one) into one MMA along N when
+ * 3 (4) Cout <= 256: the 64-channel layers, whose cost is the A-operand fetch.  Enabled by default. */
 int rrv_tc_tune_merge(int enable);
 /* KernelFilter fold (apply_filter, style_network_global.py:194-217; per frame in test/style_network_frame.py:97-105): the two
  * predicted 32x32 matrices wf1, wf2 ([out][in], fp32) are multiplied into the filter's down_sample (512 -> 32) and upsample

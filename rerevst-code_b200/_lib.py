@@ -46,8 +46,7 @@ SIGNATURES = {
     "rrv_conv2d": (C.c_int, [C.POINTER(Conv), C.c_int, _vp]),
     "rrv_tc_weight_bytes": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "rrv_pack_weights_tc": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
-    "rrv_tc_tune": (C.c_int, [C.c_int, C.c_int, C.c_int]),
-    "rrv_tc_tune2": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "rrv_tc_tune": (C.c_int, [C.c_int, C.c_int]),
     "rrv_tc_tune_pair": (C.c_int, [C.c_int, C.c_int]),
     "rrv_tc_tune_merge": (C.c_int, [C.c_int]),
     "rrv_pack_weights_f32": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),

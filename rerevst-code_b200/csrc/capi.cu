@@ -32,8 +32,7 @@ int conv2d_ffma(const rrv_conv* p, cudaStream_t st);
 int conv2d_tc(const rrv_conv* p, cudaStream_t st);
 long long tc_weight_bytes(int Cin, int Cout, int ksize, int ups);
 int pack_weights_tc(const float* w, int Cin, int Cout, int ksize, int ups, void* blob, cudaStream_t st);
-int tc_tune(int max_bn, int tile_w, int max_stages);
-int tc_tune2(int version, int mt, int ups_v1);
+int tc_tune(int max_bn, int mt);
 int tc_tune_pair(int enable, int min_bn);
 int tc_tune_merge(int enable);
 int first_layer(const void* src, int src_kind, int gray, int N, int H, int W, const float* w, const float* bias,
@@ -90,8 +89,7 @@ int64_t rrv_tc_weight_bytes(int Cin, int Cout, int ksize, int ups) { return tc_w
 int rrv_pack_weights_tc(const float* w, int Cin, int Cout, int ksize, int ups, void* blob, void* stream) {
     return pack_weights_tc(w, Cin, Cout, ksize, ups, blob, ST(stream));
 }
-int rrv_tc_tune(int max_bn, int tile_w, int max_stages) { return tc_tune(max_bn, tile_w, max_stages); }
-int rrv_tc_tune2(int version, int mt, int ups_v1) { return tc_tune2(version, mt, ups_v1); }
+int rrv_tc_tune(int max_bn, int mt) { return tc_tune(max_bn, mt); }
 int rrv_tc_tune_pair(int enable, int min_bn) { return tc_tune_pair(enable, min_bn); }
 int rrv_tc_tune_merge(int enable) { return tc_tune_merge(enable); }
 int rrv_pack_weights_f32(const float* w, int Cin, int Cout, int ksize, int Cin_pad, int Cout_pad, float* out, void* stream) {

@@ -6,13 +6,15 @@
 // (:52-55, :116-122, :364), which run in the epilogue (rrv_common.cuh: apply_epilogue).
 //
 // GEMM view: D[M = 128 output pixels][N = Cout tile] += A[M][K] * B[N][K]^T with K = taps x Cin.
-//   A  one TMA box per (tap, 64-channel chunk): a TH x TW window of the NHWC input shifted by the
-//      tap offset; rows outside the image are zero-filled by TMA, which IS the conv's zero padding.
-//      The box lands in shared memory as 128 rows of 128 bytes with the 128-byte swizzle, i.e. the
-//      canonical K-major operand layout of tcgen05.mma -- no im2col buffer anywhere.
-//   B  weights repacked once at load time to [tap][Cout][Cin] bf16, one TMA box per k-step.
+//   A  TMA boxes of the NHWC input itself (64-channel chunks); rows / columns outside the image are
+//      zero-filled by TMA, which IS the conv's zero padding.  The box lands in shared memory as rows
+//      of 128 bytes with the 128-byte swizzle, i.e. the canonical K-major operand layout of
+//      tcgen05.mma -- no im2col buffer anywhere.  One box serves several taps: the tap only moves
+//      the operand descriptor's start address by whole swizzle atoms (see the three main-loop
+//      shapes at conv_tc2_kernel / conv2d_tc2).
+//   B  weights repacked once at load time to [tap][Cout][Cin] bf16, TMA boxes per k-chunk.
 //   D  fp32 accumulators in TMEM, double buffered so the epilogue of tile i overlaps the MMAs of
-//      tile i+1.  Persistent CTAs (one per SM) walk the tile list.
+//      tile i+1.  Persistent CTAs (one per SM, or CTA pairs with cta_group::2) walk the tile list.
 // fp32 accuracy ("x3"): every fp32 operand v is carried as hi = bf16(v), lo = bf16(v - hi) and each
 // k-slice issues Ahi*Bhi + Ahi*Blo + Alo*Bhi into the same accumulator (the dropped lo*lo term is
 // 2^-18 relative).  With lo == NULL a single bf16 MMA is issued (BASELINE config 3).
@@ -20,8 +22,9 @@
 // to a 2x2 conv over the low-resolution input with summed weights (9 -> 4 taps); the four phases
 // are four GEMMs over the same low-res tile that scatter to interleaved output pixels.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) and TMEM owner,
-// warps 2..9 = epilogue (tcgen05.ld -> fused pointwise chain -> 16-byte stores); the per-channel
-// constants of the chain are gathered once per CTA into a shared-memory table.
+// warps 2..9 = epilogue (tcgen05.ld -> fused pointwise chain -> stores; the merged-tap layers stage
+// their rows in shared memory and leave through TMA stores); the per-channel constants of the chain
+// are gathered once per CTA into a shared-memory table.
 #include <cuda.h>
 #include <math_constants.h>
 
@@ -65,8 +68,7 @@ namespace {
 
 constexpr int BM = 128;          // output pixels per tile (= TMEM lanes)
 constexpr int BK = 64;           // channels per k-step (128-byte rows)
-constexpr int A_BYTES = BM * BK * 2;
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 8;       // A-operand ring slots (barrier arrays)
 constexpr int EPI_WARPS = 8;      // two per TMEM lane quadrant, alternating CW-column chunks
 constexpr int CW = 32;            // epilogue chunk width (accumulator columns per tcgen05.ld)
 constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;
@@ -75,12 +77,8 @@ constexpr int SMEM_LIMIT = 227 * 1024 - 1024;   // dynamic part: the opt-in maxi
 
 struct TcTune {
     int max_bn = 256;
-    int tile_w = 16;        // v1 only
-    int max_stages = 6;     // v1 only
-    int version = 2;        // main loop: 1 = one box per tap, 2 = row-reuse / shared weight tiles
-    int mt = 2;             // v2: M tiles (128 pixels each) per weight tile
-    int ups_v1 = 0;         // 1: nearest-x2 convolutions use the v1 main loop
-    int dxm = 1;            // v2: merge the three dx taps along N when 3 Cout_pad <= 256 (the 64-channel layers, the RGB head)
+    int mt = 2;             // M tiles (128 pixels each) per weight tile
+    int dxm = 1;            // merge the three dx taps along N when 3 Cout_pad <= 256 (the 64-channel layers, the RGB head)
     int pair = 1;           // v2: CTA pairs (cta_group::2) for Cout tiles >= pair_min_bn
     int pair_min_bn = 64;   // (<= 64 also overrides resident weights: measured faster on the 64 -> 64 layers)
 };
@@ -95,56 +93,6 @@ struct OutDesc {
     void* out_img;                       // RRV_OUT_BGR_*: the post-processed, cropped HWC BGR frame
     int crop_y0, crop_x0, crop_h, crop_w;
 };
-
-struct TcParams {
-    OutDesc o;
-    int N, H, W;            // output
-    int in_H, in_W;         // input (H/2, W/2 when ups)
-    int Cout, Cout_pad;
-    int kchunks;            // Cin / 64
-    int ntaps;              // taps per phase: 9, 1, or 4 (ups)
-    int nphase;             // 1, or 4 (ups)
-    int ksize;
-    int tiles_x, tiles_y, n_ntiles, total_tiles;
-    int tw_shift;           // TW = 1 << tw_shift, TH = 128 >> tw_shift
-    int BN;
-    int stages;
-    int x3;
-    int acc_stride, tmem_cols;
-    EpiDev ep;
-};
-
-struct TileCoord {
-    int n, y0, x0, n0, py, px, phase;
-};
-
-__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int t) {
-    TileCoord c;
-    c.phase = t % p.nphase; t /= p.nphase;
-    const int nt = t % p.n_ntiles; t /= p.n_ntiles;
-    const int tx = t % p.tiles_x; t /= p.tiles_x;
-    const int ty = t % p.tiles_y;
-    c.n = t / p.tiles_y;
-    c.y0 = ty * (BM >> p.tw_shift);
-    c.x0 = tx << p.tw_shift;
-    c.n0 = nt * p.BN;
-    c.py = c.phase >> 1;
-    c.px = c.phase & 1;
-    return c;
-}
-
-__device__ __forceinline__ void tap_offset(const TcParams& p, const TileCoord& c, int t, int& oy, int& ox) {
-    if (p.nphase == 4) {          // 2x2 taps of one upsample phase
-        oy = c.py - 1 + (t >> 1);
-        ox = c.px - 1 + (t & 1);
-    } else if (p.ksize == 3) {
-        oy = t / 3 - 1;
-        ox = t % 3 - 1;
-    } else {
-        oy = 0;
-        ox = 0;
-    }
-}
 
 // Shared-memory table of the per-channel constants of the fused pointwise chain, one array of
 // Cout_pad floats per constant (absent stages get their identity values).
@@ -704,145 +652,6 @@ __device__ __forceinline__ void epilogue_chunk_pool(const OutDesc& o, const EpiD
     split8(x, hi, lo);
     *reinterpret_cast<uint4*>(o.out_hi + px.out_off + cb + sub * 8) = hi;
     if (o.out_lo) *reinterpret_cast<uint4*>(o.out_lo + px.out_off + cb + sub * 8) = lo;
-}
-
-template <int FLAGS>
-__global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-               const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-               const TcParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t s_full[MAX_STAGES], s_empty[MAX_STAGES], s_tfull[2], s_tempty[2];
-    __shared__ uint32_t s_tmem_base;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t b_bytes = (uint32_t)p.BN * 128u;
-    const uint32_t stage_bytes = (p.x3 ? 2u : 1u) * ((uint32_t)A_BYTES + b_bytes);
-    const uint32_t off_a_lo = A_BYTES;
-    const uint32_t off_b_hi = p.x3 ? 2u * A_BYTES : (uint32_t)A_BYTES;
-    const uint32_t off_b_lo = off_b_hi + b_bytes;
-    const int ksteps = p.ntaps * p.kchunks;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) {
-            ptx::mbar_init(ptx::smem_u32(&s_full[s]), 1);
-            ptx::mbar_init(ptx::smem_u32(&s_empty[s]), 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            ptx::mbar_init(ptx::smem_u32(&s_tfull[a]), 1);
-            ptx::mbar_init(ptx::smem_u32(&s_tempty[a]), EPI_WARPS);     // one arrival per epilogue warp
-        }
-        ptx::fence_barrier_init();
-    }
-    if (warp == 0 && lane == 0) {
-        ptx::prefetch_tmap(&map_a_hi);
-        ptx::prefetch_tmap(&map_b_hi);
-        if (p.x3) {
-            ptx::prefetch_tmap(&map_a_lo);
-            ptx::prefetch_tmap(&map_b_lo);
-        }
-    }
-    float* s_tab = reinterpret_cast<float*>(smem_raw + (smem_base - ptx::smem_u32(smem_raw)) + (uint32_t)p.stages * stage_bytes);
-    fill_epilogue_table(s_tab, p.ep, p.Cout, p.Cout_pad, TC_THREADS);
-    if (warp == 1) {
-        ptx::tmem_alloc(ptx::smem_u32(&s_tmem_base), (uint32_t)p.tmem_cols);
-        ptx::tmem_relinquish();
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    ptx::tc_fence_after();
-    const uint32_t tmem_base = s_tmem_base;
-
-    if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord c = decode_tile(p, tile);
-                for (int t = 0; t < p.ntaps; ++t) {
-                    int oy, ox;
-                    tap_offset(p, c, t, oy, ox);
-                    const int tb = t;                                    // blob order = PyTorch tap order (dy * 3 + dx)
-                    const int brow = (c.phase * p.ntaps + tb) * p.Cout_pad + c.n0;
-                    for (int kc = 0; kc < p.kchunks; ++kc) {
-                        ptx::mbar_wait(ptx::smem_u32(&s_empty[stage]), phase ^ 1u);
-                        const uint32_t full = ptx::smem_u32(&s_full[stage]);
-                        const uint32_t sb = smem_base + (uint32_t)stage * stage_bytes;
-                        ptx::mbar_expect_tx(full, stage_bytes);
-                        ptx::tma_load_4d(sb, &map_a_hi, full, kc * BK, c.x0 + ox, c.y0 + oy, c.n);
-                        ptx::tma_load_2d(sb + off_b_hi, &map_b_hi, full, kc * BK, brow);
-                        if (p.x3) {
-                            ptx::tma_load_4d(sb + off_a_lo, &map_a_lo, full, kc * BK, c.x0 + ox, c.y0 + oy, c.n);
-                            ptx::tma_load_2d(sb + off_b_lo, &map_b_lo, full, kc * BK, brow);
-                        }
-                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        const uint32_t idesc = ptx::make_idesc_bf16(BM, p.BN);
-        int stage = 0;
-        uint32_t phase = 0;
-        int as = 0;
-        uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            ptx::mbar_wait(ptx::smem_u32(&s_tempty[as]), aphase ^ 1u);
-            ptx::tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.acc_stride);
-            for (int ks = 0; ks < ksteps; ++ks) {
-                ptx::mbar_wait(ptx::smem_u32(&s_full[stage]), phase);
-                ptx::tc_fence_after();
-                const uint32_t sb = smem_base + (uint32_t)stage * stage_bytes;
-                const uint32_t empty_bar = ptx::smem_u32(&s_empty[stage]), tfull_bar = ptx::smem_u32(&s_tfull[as]);
-                if (ptx::elect_one()) {
-                    ptx::mma_kblock(d_tmem, sb, sb + off_a_lo, sb + off_b_hi, sb + off_b_lo, idesc, p.x3 ? 3u : 0u, ks == 0);
-                    ptx::mma_commit(empty_bar);                               // frees the smem slot when the MMAs retire
-                    if (ks == ksteps - 1) ptx::mma_commit(tfull_bar);
-                }
-                __syncwarp();
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-            }
-            if (++as == 2) { as = 0; aphase ^= 1u; }
-        }
-    } else {
-        // ================= epilogue (warps 2..9; TMEM lane quadrant = warp % 4) =================
-        const int quad = warp & 3;
-        const int half = (warp - 2) >> 2;                 // which 32-column chunks this warp takes
-        const int m = quad * 32 + lane;
-        const int ty = m >> p.tw_shift, tx = m & ((1 << p.tw_shift) - 1);
-        const int nchunks = (p.BN + CW - 1) / CW;
-        const EpiDev& e = p.ep;
-        int as = 0;
-        uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const TileCoord c = decode_tile(p, tile);
-            const int iy = c.y0 + ty, ix = c.x0 + tx;
-            const bool valid = iy < p.in_H && ix < p.in_W;
-            const int oy = p.nphase == 4 ? 2 * iy + c.py : iy;
-            const int ox = p.nphase == 4 ? 2 * ix + c.px : ix;
-            ptx::mbar_wait(ptx::smem_u32(&s_tfull[as]), aphase);
-            ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t)(as * p.acc_stride) + ((uint32_t)(quad * 32) << 16);
-            const PixCtx px = make_pix(p.o, e, c.n, oy, ox, valid);
-            for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4)
-                epilogue_chunk<FLAGS, 0>(p.o, e, s_tab, p.Cout_pad, taddr + (uint32_t)(ch * CW), px, c.n0 + ch * CW, ch * CW, p.BN);
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&s_tempty[as]));
-            if (++as == 2) { as = 0; aphase ^= 1u; }
-        }
-    }
-
-    ptx::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
-    }
 }
 
 // =====================================================================================================
@@ -1621,12 +1430,6 @@ OutDesc make_out(const rrv_conv* p) {
     return o;
 }
 
-int pick_bn(int Cout_pad) {
-    int bn = std::min(Cout_pad, g_tune.max_bn);
-    while (bn > 16 && Cout_pad % bn != 0) bn -= 16;
-    return bn;
-}
-
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -1641,19 +1444,6 @@ int num_sms() {
 
 int epi_flags(const rrv_epilogue& e) {
     return (e.norm1 ? EPI_N1 : 0) | (e.res_hi ? EPI_RES : 0) | (e.norm2 ? EPI_N2 : 0) | (e.affine ? EPI_AFF : 0);
-}
-
-template <int FLAGS>
-int launch_tc1(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& mb_hi,
-               const CUtensorMap& mb_lo, const TcParams& d) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        const cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<FLAGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-        RRV_REQUIRE(e == cudaSuccess, "cudaFuncSetAttribute(conv_tc_kernel): %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
-    conv_tc_kernel<FLAGS><<<grid, TC_THREADS, smem, st>>>(ma_hi, ma_lo, mb_hi, mb_lo, d);
-    return check_launch("conv_tc_kernel");
 }
 
 // (the two output maps of the staged TMA stores travel in file-scope slots set by conv2d_tc2 right before the launch: every
@@ -2005,13 +1795,11 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
 
 }  // namespace
 
-int tc_tune(int max_bn, int tile_w, int max_stages) {
+int tc_tune(int max_bn, int mt) {
     RRV_REQUIRE(max_bn >= 16 && max_bn <= 256 && max_bn % 16 == 0, "rrv_tc_tune: max_bn must be a multiple of 16 in [16, 256]");
-    RRV_REQUIRE(tile_w == 8 || tile_w == 16 || tile_w == 32 || tile_w == 64 || tile_w == 128, "rrv_tc_tune: tile_w must be 8..128, power of 2");
-    RRV_REQUIRE(max_stages >= 2 && max_stages <= MAX_STAGES, "rrv_tc_tune: max_stages must be in [2, %d]", MAX_STAGES);
+    RRV_REQUIRE(mt == 1 || mt == 2, "rrv_tc_tune: mt must be 1 or 2");
     g_tune.max_bn = max_bn;
-    g_tune.tile_w = tile_w;
-    g_tune.max_stages = max_stages;
+    g_tune.mt = mt;
     return 0;
 }
 
@@ -2024,15 +1812,6 @@ int tc_tune_pair(int enable, int min_bn) {
 
 int tc_tune_merge(int enable) {
     g_tune.dxm = enable ? 1 : 0;
-    return 0;
-}
-
-int tc_tune2(int version, int mt, int ups_v1) {
-    RRV_REQUIRE(version == 1 || version == 2, "rrv_tc_tune2: version must be 1 or 2");
-    RRV_REQUIRE(mt == 1 || mt == 2, "rrv_tc_tune2: mt must be 1 or 2");
-    g_tune.version = version;
-    g_tune.mt = mt;
-    g_tune.ups_v1 = ups_v1 ? 1 : 0;
     return 0;
 }
 
@@ -2077,7 +1856,6 @@ int conv2d_tc(const rrv_conv* p, cudaStream_t st) {
         RRV_REQUIRE(p->crop_h > 0 && p->crop_w > 0 && p->crop_y0 >= 0 && p->crop_x0 >= 0 && p->crop_y0 + p->crop_h <= p->H &&
                         p->crop_x0 + p->crop_w <= p->W,
                     "rrv_conv2d: crop window (%d,%d,%d,%d) outside the %dx%d result", p->crop_y0, p->crop_x0, p->crop_h, p->crop_w, p->H, p->W);
-        RRV_REQUIRE(g_tune.version == 2, "rrv_conv2d: the BGR frame output needs the v2 main loop");
     } else {
         RRV_REQUIRE(p->out_mode == RRV_OUT_F32_NHWC || p->out_mode == RRV_OUT_F32_NCHW, "rrv_conv2d: unknown out_mode %d", p->out_mode);
         RRV_REQUIRE(p->out_f32 != nullptr, "rrv_conv2d: out_f32 is NULL");
@@ -2085,74 +1863,17 @@ int conv2d_tc(const rrv_conv* p, cudaStream_t st) {
     }
     RRV_REQUIRE(p->terms >= RRV_TERMS_FULL && p->terms <= RRV_TERMS_NO_ALO, "rrv_conv2d: bad terms %d", p->terms);
     if (p->stats != nullptr) {
-        RRV_REQUIRE(g_tune.version == 2 && !(ups && g_tune.ups_v1), "rrv_conv2d(stats): needs the v2 main loop");
         RRV_REQUIRE(!p->pool && epi_flags(p->ep) == 0, "rrv_conv2d(stats): only bias + activation may precede the fused statistics");
         RRV_REQUIRE(p->out_mode == RRV_OUT_PLANES || p->out_mode == RRV_OUT_F32_NHWC, "rrv_conv2d(stats): planes or NHWC output");
     }
 
     if (p->pool) {
-        RRV_REQUIRE(!ups && p->out_mode == RRV_OUT_PLANES && p->Cout % 32 == 0 && g_tune.version == 2,
-                    "rrv_conv2d(pool): needs a plain (not upsampling) convolution, planes output, Cout %% 32 == 0 and the v2 main loop");
+        RRV_REQUIRE(!ups && p->out_mode == RRV_OUT_PLANES && p->Cout % 32 == 0,
+                    "rrv_conv2d(pool): needs a plain (not upsampling) convolution, planes output and Cout %% 32 == 0");
         RRV_REQUIRE(epi_flags(p->ep) == 0, "rrv_conv2d(pool): only bias + activation may precede the fused max-pool");
         RRV_REQUIRE(p->H >= 2 && p->W >= 2, "rrv_conv2d(pool): empty pooled output");
     }
-    if (g_tune.version == 2 && !(ups && g_tune.ups_v1)) return conv2d_tc2(p, st);
-
-    TcParams d;
-    d.N = p->N; d.H = p->H; d.W = p->W;
-    d.in_H = p->H >> ups; d.in_W = p->W >> ups;
-    d.Cout = p->Cout;
-    d.Cout_pad = cout_pad_of(p->Cout);
-    d.kchunks = p->Cin / BK;
-    d.ksize = p->ksize;
-    d.nphase = ups ? 4 : 1;
-    d.ntaps = ups ? 4 : p->ksize * p->ksize;
-    d.BN = pick_bn(d.Cout_pad);
-    d.n_ntiles = d.Cout_pad / d.BN;
-    int tw = g_tune.tile_w;
-    while (tw > 8 && tw / 2 >= d.in_W) tw /= 2;                  // narrow images: fewer wasted columns
-    d.tw_shift = 0;
-    while ((1 << d.tw_shift) < tw) ++d.tw_shift;
-    const int th = BM / tw;
-    d.tiles_x = ceil_div(d.in_W, tw);
-    d.tiles_y = ceil_div(d.in_H, th);
-    const long long total = (long long)d.N * d.tiles_y * d.tiles_x * d.n_ntiles * d.nphase;
-    RRV_REQUIRE(total < (1LL << 31), "rrv_conv2d: too many tiles");
-    d.total_tiles = (int)total;
-    d.x3 = p->in_lo != nullptr;
-    const int stage_bytes = (d.x3 ? 2 : 1) * (A_BYTES + d.BN * 128);
-    const int tab_bytes = d.Cout_pad * TAB_BYTES;
-    d.stages = std::min(g_tune.max_stages, (SMEM_LIMIT - 1024 - tab_bytes) / stage_bytes);
-    RRV_REQUIRE(d.stages >= 2, "rrv_conv2d(tcgen05): tile does not fit shared memory (BN=%d)", d.BN);
-    d.acc_stride = (d.BN + 31) / 32 * 32;
-    d.tmem_cols = 32;
-    while (d.tmem_cols < 2 * d.acc_stride) d.tmem_cols *= 2;
-    d.o = make_out(p);
-    d.ep = make_epi(p->ep, p->Cout);
-    d.ep.lo_fp16 = 0;
-
-    CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
-    const int rows = d.nphase * d.ntaps * d.Cout_pad;
-    const uint16_t* w_hi = (const uint16_t*)p->w_tc;
-    const uint16_t* w_lo = w_hi + (long long)rows * p->Cin;
-    if (encode_act_map(&ma_hi, p->in_hi, d.N, d.in_H, d.in_W, p->Cin, tw, th)) return 1;
-    if (encode_w_map(&mb_hi, w_hi, rows, p->Cin, d.BN)) return 1;
-    if (d.x3) {
-        if (encode_act_map(&ma_lo, p->in_lo, d.N, d.in_H, d.in_W, p->Cin, tw, th)) return 1;
-        if (encode_w_map(&mb_lo, w_lo, rows, p->Cin, d.BN)) return 1;
-    } else {
-        ma_lo = ma_hi;
-        mb_lo = mb_hi;
-    }
-
-    const int smem = d.stages * stage_bytes + tab_bytes + 1024;
-    const int grid = std::min(d.total_tiles, num_sms());
-    const bool plain_out = p->out_mode == RRV_OUT_PLANES || p->out_mode == RRV_OUT_F32_NHWC;
-    switch (plain_out ? epi_flags(p->ep) : -1) {
-        case 0: return launch_tc1<0>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
-        case EPI_N1: return launch_tc1<EPI_N1>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
-        default: return launch_tc1<-1>(grid, smem, st, ma_hi, ma_lo, mb_hi, mb_lo, d);
-    }
+    return conv2d_tc2(p, st);
 }
 
 }  // namespace rrv

@@ -85,7 +85,9 @@ def main(style_img="./inputs/plum_flower.jpg", content_video="./inputs/ambush_4/
     first = cv2.imread(frame_list[0]) if frame_num else None
     pad_to = padded_size(first.shape[0], first.shape[1]) if first is not None else None
     raw_frames = (cv2.imread(frame_list[i]) for i in range(frame_num))
-    for i, styled in enumerate(framework.transfer_stream(raw_frames, pad_to=pad_to, copy=False)):     # written out before the next one
+    # out_dtype="u8": the frame arrives as the uint8 image cv2.imwrite would make of the reference's float32 result (:170,
+    # saturate_cast<uchar>(cvRound(v))) -- the same file, a quarter of the download
+    for i, styled in enumerate(framework.transfer_stream(raw_frames, pad_to=pad_to, copy=False, out_dtype="u8")):     # written out before the next one
         say("Stylizing frame %d" % i)
         cv2.imwrite(os.path.join(out_dir, os.path.basename(frame_list[i])), styled)
 

@@ -28,3 +28,24 @@ def state_dict():
     from rerevst_code_b200.weights import synthetic_state_dict
     from oracle import cases
     return synthetic_state_dict(cases.WEIGHT_SEED)
+
+
+@pytest.fixture(autouse=True)
+def _reset_kernel_tuning():
+    """The tensor-core kernel's tuning knobs (rrv_tc_tune*) are process-global: a test that flips them and then fails must not
+    leave the library mis-tuned for the tests that follow."""
+    yield
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return
+        from rerevst_code_b200 import _lib
+        if _lib._lib is None:
+            return
+        lib = _lib._lib
+        lib.rrv_tc_tune(256, 2)
+        lib.rrv_tc_tune_pair(1, 64)
+        lib.rrv_tc_tune_merge(1)
+        lib.rrv_set_lo_format(0)
+    except Exception:
+        pass

@@ -558,13 +558,14 @@ def test_temporal_loss_and_backward(dev):
 
 # ---------------------------------------------------------------------------------- kernel variants / entry point
 
-@pytest.mark.parametrize("tune", [(1, 2, 0, 1), (2, 1, 0, 1), (2, 2, 1, 1), (2, 2, 0, 0)])
+@pytest.mark.parametrize("tune", [(256, 1, 1, 1), (128, 2, 1, 1), (256, 2, 0, 1), (256, 2, 1, 0), (64, 1, 0, 0)])
 def test_conv_main_loop_variants(L, dev, tune):
-    """rrv_tc_tune2 / rrv_tc_tune_pair: v1 (one box per tap), v2 with one M tile per weight tile, ups through v1,
-    v2 without CTA pairs (the defaults -- v2, two M tiles, pairs -- run in every other test)."""
+    """rrv_tc_tune / rrv_tc_tune_pair / rrv_tc_tune_merge: one M tile per weight tile, narrower Cout tiles, no CTA pairs, no merged
+    taps (the defaults -- 256-wide tiles, two M tiles, pairs, merged taps -- run in every other test)."""
     from rerevst_code_b200.engine import ConvW, make_epilogue
-    L.check(L.lib().rrv_tc_tune2(*tune[:3]))
-    L.check(L.lib().rrv_tc_tune_pair(tune[3], 128))
+    L.check(L.lib().rrv_tc_tune(tune[0], tune[1]))
+    L.check(L.lib().rrv_tc_tune_pair(tune[2], 128))
+    L.check(L.lib().rrv_tc_tune_merge(tune[3]))
     try:
         for case in [(1, 40, 24, 64, 64, 3, 0), (2, 36, 20, 128, 128, 3, 0), (1, 48, 32, 128, 64, 3, 1), (1, 40, 16, 256, 256, 3, 1),
                      (1, 33, 17, 64, 128, 1, 0)]:
@@ -590,8 +591,9 @@ def test_conv_main_loop_variants(L, dev, tune):
             L.check(L.lib().rrv_conv2d(C.byref(d), L.IMPL_TCGEN05, L.stream()), str(case))
             assert rel_linf(out.permute(0, 3, 1, 2).cpu(), ref) < 2e-4, (tune, case)
     finally:
-        L.check(L.lib().rrv_tc_tune2(2, 2, 0))
+        L.check(L.lib().rrv_tc_tune(256, 2))
         L.check(L.lib().rrv_tc_tune_pair(1, 64))
+        L.check(L.lib().rrv_tc_tune_merge(1))
 
 
 @pytest.mark.parametrize("case", [(1, 64, 40, 64, 64), (2, 37, 21, 64, 64), (1, 32, 48, 128, 128), (2, 19, 27, 128, 128),

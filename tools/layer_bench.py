@@ -54,11 +54,10 @@ def bench(name, tunings, iters=5):
         d.out_mode, d.out_f32, d.out_C = L.OUT_F32_NCHW, o.data_ptr(), 3
     flops = 2.0 * Cin * Cout * k * k * H * W
     res = []
-    for label, (ver, mt, upsv1, pair, minbn, maxbn, *rest) in tunings.items():
+    for label, (mt, pair, minbn, maxbn, *rest) in tunings.items():
         L.check(L.lib().rrv_tc_tune_merge(rest[0] if rest else 1))
-        L.check(L.lib().rrv_tc_tune2(ver, mt, upsv1))
         L.check(L.lib().rrv_tc_tune_pair(pair, minbn))
-        L.check(L.lib().rrv_tc_tune(maxbn, 16, 6))
+        L.check(L.lib().rrv_tc_tune(maxbn, mt))
         for _ in range(2):
             L.check(L.lib().rrv_conv2d(C.byref(d), 1, L.stream()))
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -74,13 +73,13 @@ def bench(name, tunings, iters=5):
 
 if __name__ == "__main__":
     if "--small" in sys.argv:
-        T = {"default": (2, 2, 0, 1, 64, 256), "mt1": (2, 1, 0, 1, 64, 256), "bn128": (2, 2, 0, 1, 64, 128), "mt1_bn128": (2, 1, 0, 1, 64, 128),
-             "mt1_bn64": (2, 1, 0, 1, 64, 64)}
+        T = {"default": (2, 1, 64, 256), "mt1": (1, 1, 64, 256), "bn128": (2, 1, 64, 128), "mt1_bn128": (1, 1, 64, 128),
+             "mt1_bn64": (1, 1, 64, 64)}
         for n in [a for a in sys.argv[1:] if not a.startswith("--")]:
             bench(n, T, iters=20)
         sys.exit(0)
-    T = {"default": (2, 2, 0, 1, 64, 256), "nomerge": (2, 2, 0, 1, 64, 256, 0), "nopair": (2, 2, 0, 0, 64, 256),
-         "nopair_nomerge": (2, 2, 0, 0, 64, 256, 0), "v1": (1, 2, 1, 0, 128, 256), "pair32": (2, 2, 0, 1, 32, 256)}
+    T = {"default": (2, 1, 64, 256), "nomerge": (2, 1, 64, 256, 0), "nopair": (2, 0, 64, 256),
+         "nopair_nomerge": (2, 0, 64, 256, 0), "pair32": (2, 1, 32, 256)}
     names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(LAYERS)
     for n in names:
         bench(n, T)
