@@ -210,6 +210,14 @@ int rrv_stats_merge(const double* parts, int nparts, int C, double* merged, void
  *         style_network_frame.py:39-43).
  * kind | 16: row 2 of `part` still holds sum(x^2) (straight from a one-pass producer, no rrv_stats_sums_to_m2 in between). */
 int rrv_stats_finalize(const double* part, int C, int kind, float eps, float* out, void* stream);
+/* FilterPredictor's content / style term (style_network_global.py:150-172; per frame in style_network_frame.py:53-62) is
+ * mean_{n,y,x}(conv3x3(x) + b): only the MEAN of a 512 -> 32 convolution.  The convolution is linear, so that mean follows from
+ * nine per-channel sums of x (total, first / last row and column, corners: each tap reads everything but one border row and
+ * column) and one dot product per output -- one read of x instead of the convolution.  x: planes [N][H][W][Cin]; w: fp32 OIHW
+ * [Cout][Cin][3][3]; scratch: double[9][Cin]; part: double[5][Cout] = {N H W, sum over all output pixels, 0, 0, 0}, a partial
+ * that rrv_stats_merge / rrv_stats_finalize(kind 2) accept. */
+int rrv_conv3x3_output_sum(const void* in_hi, const void* in_lo, int N, int H, int W, int Cin, const float* w_oihw,
+                           const float* bias, int Cout, double* scratch, double* part, void* stream);
 /* FilterPredictor FC (:157,169): out[1024] = W[1024][64] . concat(c[32], s[32]) + b. */
 int rrv_filter_fc(const float* w, const float* b, const float* c_mean, const float* s_mean,
                   float* out, void* stream);

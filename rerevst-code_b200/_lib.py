@@ -63,6 +63,7 @@ SIGNATURES = {
     "rrv_postprocess_bgr": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rrv_postprocess_bgr_u8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rrv_channel_stats": (C.c_int, [_vp, _i64, C.c_int, _vp, _vp]),
+    "rrv_conv3x3_output_sum": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "rrv_stats_init": (C.c_int, [_vp, C.c_int, C.c_double, _vp]),
     "rrv_stats_sums_to_m2": (C.c_int, [_vp, C.c_int, _vp]),
     "rrv_pointwise_stats": (C.c_int, [_vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Epilogue), C.c_int,

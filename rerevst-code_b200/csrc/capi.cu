@@ -52,6 +52,8 @@ int fold_filter(const float* wf1, const float* wf2, const float* down_w, const f
                 float* down_bias, void* up_blob, cudaStream_t st);
 int channel_stats(const float* x, long long npix, int C, double* part, cudaStream_t st);
 int stats_init(double* part, int C, double count, cudaStream_t st);
+int conv3x3_output_sum(const void* in_hi, const void* in_lo, int N, int H, int W, int Cin, const float* w_oihw, const float* bias,
+                       int Cout, double* scratch, double* part, cudaStream_t st);
 int stats_sums_to_m2(double* part, int C, cudaStream_t st);
 int stats_merge(const double* parts, int nparts, int C, double* merged, cudaStream_t st);
 int stats_finalize(const double* part, int C, int kind, float eps, float* out, cudaStream_t st);
@@ -123,6 +125,10 @@ int rrv_pointwise_stats(const float* in, int64_t in_bs, int N, int H, int W, int
                         void* out_hi, void* out_lo, float* out_f32, double* stats, int stats_minmax, void* stream) {
     RRV_REQUIRE(stats != nullptr, "rrv_pointwise_stats: stats is NULL");
     return pointwise(in, in_bs, N, H, W, C, ep, out_mode, out_hi, out_lo, out_f32, stats, stats_minmax, ST(stream));
+}
+int rrv_conv3x3_output_sum(const void* in_hi, const void* in_lo, int N, int H, int W, int Cin, const float* w_oihw,
+                           const float* bias, int Cout, double* scratch, double* part, void* stream) {
+    return conv3x3_output_sum(in_hi, in_lo, N, H, W, Cin, w_oihw, bias, Cout, scratch, part, ST(stream));
 }
 int rrv_stats_init(double* part, int C, double count, void* stream) { return stats_init(part, C, count, ST(stream)); }
 int rrv_stats_sums_to_m2(double* part, int C, void* stream) { return stats_sums_to_m2(part, C, ST(stream)); }

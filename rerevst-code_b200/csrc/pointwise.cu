@@ -64,8 +64,10 @@ int maxpool2x2(const void* in_hi, const void* in_lo, int N, int H, int W, int C,
 // loads (+ the residual), ~10 FP32 operations per value, the hi / lo split and two 16-byte stores -- an HBM-bound pass.
 // STATS: the per-channel {sum, sum of squares[, min, max]} of the values written also go to `stats` (double[5][C]): fp32 per thread
 // (a few dozen pixels), then double across the block's threads of equal group through shared memory, one atomic per channel.
-template <bool STATS>
-__global__ void __launch_bounds__(256, 2) pointwise_kernel(const float* __restrict__ in, long long in_bs, int N, int H, int W,
+// KIND fixes the set of stages at compile time so that only their constants occupy registers (occupancy is what an HBM-bound
+// pass lives on): 0 = norm1; 1 = norm1 + affine (AdaIN); 2 = norm1 + residual; 3 = residual only; 4 = whatever `ep` says.
+template <bool STATS, int KIND>
+__global__ void __launch_bounds__(256, (KIND == 4 || STATS) ? 2 : 3) pointwise_kernel(const float* __restrict__ in, long long in_bs, int N, int H, int W,
                                                         int C, EpiDev ep, int out_mode, uint16_t* out_hi,
                                                         uint16_t* out_lo, float* out_f32, double* stats, int stats_minmax) {
     constexpr int V = 4;                      // channels per thread: 16-byte loads, and the constants below fit ~90 registers
@@ -79,22 +81,28 @@ __global__ void __launch_bounds__(256, 2) pointwise_kernel(const float* __restri
 #pragma unroll
         for (int k = 0; k < V; ++k) { ssum[k] = 0.0f; ssq[k] = 0.0f; smn[k] = CUDART_INF_F; smx[k] = -CUDART_INF_F; }
     }
+    // which stages exist: compile-time for KIND < 4 (the host guarantees the match), from `ep` otherwise
+    const bool has_bias = KIND == 4 && ep.bias != nullptr, has_act = KIND == 4 && ep.act != 0;
+    const bool has_n1 = KIND <= 2 || (KIND == 4 && ep.norm1 != nullptr);
+    const bool has_res = KIND == 2 || KIND == 3 || (KIND == 4 && ep.res_hi != nullptr);
+    const bool has_n2 = KIND == 4 && ep.norm2 != nullptr;
+    const bool has_aff = KIND == 1 || (KIND == 4 && ep.affine != nullptr);
     // per-channel constants, once per thread
     float bias[V], m1[V], r1[V], lo1[V], hi1[V], m2[V], r2[V], lo2[V], hi2[V], sc[V], sh[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) {
         const int c = c0 + k;
-        bias[k] = ep.bias ? __ldg(ep.bias + c) : 0.0f;
-        m1[k] = ep.norm1 ? __ldg(ep.norm1 + c) : 0.0f;
-        r1[k] = ep.norm1 ? __ldg(ep.norm1 + C + c) : 1.0f;
-        lo1[k] = ep.norm1 ? __ldg(ep.norm1 + 2 * C + c) : -CUDART_INF_F;
-        hi1[k] = ep.norm1 ? __ldg(ep.norm1 + 3 * C + c) : CUDART_INF_F;
-        m2[k] = ep.norm2 ? __ldg(ep.norm2 + c) : 0.0f;
-        r2[k] = ep.norm2 ? __ldg(ep.norm2 + C + c) : 1.0f;
-        lo2[k] = ep.norm2 ? __ldg(ep.norm2 + 2 * C + c) : -CUDART_INF_F;
-        hi2[k] = ep.norm2 ? __ldg(ep.norm2 + 3 * C + c) : CUDART_INF_F;
-        sc[k] = ep.affine ? __ldg(ep.affine + c) : 1.0f;
-        sh[k] = ep.affine ? __ldg(ep.affine + C + c) : 0.0f;
+        bias[k] = has_bias ? __ldg(ep.bias + c) : 0.0f;
+        m1[k] = has_n1 ? __ldg(ep.norm1 + c) : 0.0f;
+        r1[k] = has_n1 ? __ldg(ep.norm1 + C + c) : 1.0f;
+        lo1[k] = has_n1 ? __ldg(ep.norm1 + 2 * C + c) : -CUDART_INF_F;
+        hi1[k] = has_n1 ? __ldg(ep.norm1 + 3 * C + c) : CUDART_INF_F;
+        m2[k] = has_n2 ? __ldg(ep.norm2 + c) : 0.0f;
+        r2[k] = has_n2 ? __ldg(ep.norm2 + C + c) : 1.0f;
+        lo2[k] = has_n2 ? __ldg(ep.norm2 + 2 * C + c) : -CUDART_INF_F;
+        hi2[k] = has_n2 ? __ldg(ep.norm2 + 3 * C + c) : CUDART_INF_F;
+        sc[k] = has_aff ? __ldg(ep.affine + c) : 1.0f;
+        sh[k] = has_aff ? __ldg(ep.affine + C + c) : 0.0f;
     }
     // U pixels per trip: all their loads are issued before the first value is used (one 16-byte load per pixel and tensor would
     // leave too few bytes in flight per SM for an HBM-bound pass)
@@ -111,7 +119,7 @@ __global__ void __launch_bounds__(256, 2) pointwise_kernel(const float* __restri
             unsigned n = 0, rem = p;
             if (N > 1) { n = p / HW; rem = p - n * HW; }
             a[u] = __ldg(reinterpret_cast<const float4*>(in + (long long)n * in_bs + (long long)rem * C + c0));
-            if (ep.res_hi != nullptr) {
+            if (has_res) {
                 const unsigned y = rem / (unsigned)W, x = rem - y * (unsigned)W;
                 const long long off = (long long)n * ep.res_batch_stride + ((long long)(y >> ep.res_shift) * ep.res_W + (x >> ep.res_shift)) * C + c0;
                 if (ep.res_f32) {
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(256, 2) pointwise_kernel(const float* __restri
             const unsigned p = p0 + (unsigned)u * pstride;
             float v[V] = {a[u].x, a[u].y, a[u].z, a[u].w};
             float rr[V];
-            if (ep.res_hi != nullptr) {
+            if (has_res) {
                 if (ep.res_f32) {
                     rr[0] = q[u].x; rr[1] = q[u].y; rr[2] = q[u].z; rr[3] = q[u].w;
                 } else {
@@ -141,30 +149,31 @@ __global__ void __launch_bounds__(256, 2) pointwise_kernel(const float* __restri
                 }
             }
             // the chain of rrv_epilogue, in the reference's operation order (rrv_common.cuh: apply_epilogue)
-            if (ep.bias != nullptr) {
+            if (has_bias) {
 #pragma unroll
                 for (int k = 0; k < V; ++k) v[k] += bias[k];
             }
-            if (ep.act == 1) {
+            if (!has_act) {
+            } else if (ep.act == 1) {
 #pragma unroll
                 for (int k = 0; k < V; ++k) v[k] = fmaxf(v[k], 0.0f);
             } else if (ep.act == 2) {
 #pragma unroll
                 for (int k = 0; k < V; ++k) v[k] = v[k] > 0.0f ? v[k] : 0.2f * v[k];
             }
-            if (ep.norm1 != nullptr) {
+            if (has_n1) {
 #pragma unroll
                 for (int k = 0; k < V; ++k) v[k] = fminf(hi1[k], fmaxf(lo1[k], (v[k] - m1[k]) * r1[k]));
             }
-            if (ep.res_hi != nullptr) {
+            if (has_res) {
 #pragma unroll
                 for (int k = 0; k < V; ++k) v[k] += rr[k];
             }
-            if (ep.norm2 != nullptr) {
+            if (has_n2) {
 #pragma unroll
                 for (int k = 0; k < V; ++k) v[k] = fminf(hi2[k], fmaxf(lo2[k], (v[k] - m2[k]) * r2[k]));
             }
-            if (ep.affine != nullptr) {
+            if (has_aff) {
 #pragma unroll
                 for (int k = 0; k < V; ++k) v[k] = v[k] * sc[k] + sh[k];
             }
@@ -235,13 +244,32 @@ int pointwise(const float* in, long long in_bs, int N, int H, int W, int C, cons
     RRV_REQUIRE((long long)N * H * W < (1LL << 31), "rrv_pointwise: more than 2^31 pixels");
     RRV_REQUIRE(C / 4 <= 256 && 256 % (C / 4) == 0, "rrv_pointwise: C / 4 must divide 256 (C=%d)", C);     // a thread keeps its channel group
     const int grid = (int)std::min<long long>((2 * total + 255) / 256, 148LL * 16);
+    const bool plain = !ep->bias && ep->act == 0 && !ep->norm2;
+    int kind = 4;
+    if (plain && ep->norm1 && !ep->res_hi && !ep->affine) kind = 0;
+    else if (plain && ep->norm1 && !ep->res_hi && ep->affine) kind = 1;
+    else if (plain && ep->norm1 && ep->res_hi && !ep->affine) kind = 2;
+    else if (plain && !ep->norm1 && ep->res_hi && !ep->affine) kind = 3;
+    const EpiDev e = make_epi(*ep, C);
+#define RRV_PW(S, K)                                                                                                              \
+    pointwise_kernel<S, K><<<grid, 256, 0, st>>>(in, in_bs, N, H, W, C, e, out_mode, (uint16_t*)out_hi, (uint16_t*)out_lo, out_f32, \
+                                                 stats, stats_minmax)
     if (stats != nullptr) {
-        pointwise_kernel<true><<<grid, 256, 0, st>>>(in, in_bs, N, H, W, C, make_epi(*ep, C), out_mode, (uint16_t*)out_hi,
-                                                     (uint16_t*)out_lo, out_f32, stats, stats_minmax);
+        switch (kind) {
+            case 2: RRV_PW(true, 2); break;
+            case 3: RRV_PW(true, 3); break;
+            default: RRV_PW(true, 4); break;
+        }
         return check_launch("pointwise_kernel<stats>");
     }
-    pointwise_kernel<false><<<grid, 256, 0, st>>>(in, in_bs, N, H, W, C, make_epi(*ep, C), out_mode, (uint16_t*)out_hi,
-                                                  (uint16_t*)out_lo, out_f32, nullptr, 0);
+    switch (kind) {
+        case 0: RRV_PW(false, 0); break;
+        case 1: RRV_PW(false, 1); break;
+        case 2: RRV_PW(false, 2); break;
+        case 3: RRV_PW(false, 3); break;
+        default: RRV_PW(false, 4); break;
+    }
+#undef RRV_PW
     return check_launch("pointwise_kernel");
 }
 

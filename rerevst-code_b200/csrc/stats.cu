@@ -202,3 +202,137 @@ int filter_fc(const float* w, const float* b, const float* c_mean, const float* 
 }
 
 }  // namespace rrv
+
+// ---- spatial mean of a 3x3 convolution without computing the convolution ------------------------------------------------
+// FilterPredictor (style_network_global.py:150-172, style_network_frame.py:53-62) only ever uses
+// mean_{n,y,x}(conv3x3(content) + b).  The convolution is linear, so the sum over all output pixels of tap (dy, dx) is the sum
+// of the input over the pixels that tap reads: everything except the last / first row (dy = 0 / 2) and the last / first column
+// (dx = 0 / 2) -- zero padding contributes nothing.  Nine per-channel sums of the input (total, first / last row, first / last
+// column, four corners) give all nine tap sums by inclusion-exclusion, and a 64 x 4608 dot product finishes: one read of the
+// input instead of a 512 -> 64 convolution per predictor pair (0.07 ms each at 152 x 256, three per frame in frame mode).
+namespace rrv {
+
+// out: double[9][C] = {total, row 0, row H-1, col 0, col W-1, (0,0), (0,W-1), (H-1,0), (H-1,W-1)}, zero-initialised by the caller
+__global__ void __launch_bounds__(256, 3) border_sums_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, int N, int H,
+                                                          int W, int C, double* __restrict__ out) {
+    const int C8 = C >> 3;
+    const unsigned gtid = blockIdx.x * 256u + threadIdx.x, gthreads = gridDim.x * 256u;
+    const int c0 = (int)(gtid % (unsigned)C8) * 8;
+    const unsigned pstride = gthreads / (unsigned)C8;
+    const unsigned HW = (unsigned)H * (unsigned)W, npix = (unsigned)N * HW;
+    float acc[5][8];
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[q][k] = 0.0f;
+    for (unsigned pp = gtid / (unsigned)C8; pp < npix; pp += 2 * pstride) {
+      float vv[2][8];
+      const bool two = pp + pstride < npix;
+      load8(hi + (size_t)pp * C + c0, lo ? lo + (size_t)pp * C + c0 : nullptr, 0, vv[0]);       // both pixels' loads first
+      if (two) load8(hi + (size_t)(pp + pstride) * C + c0, lo ? lo + (size_t)(pp + pstride) * C + c0 : nullptr, 0, vv[1]);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !two) break;
+        const unsigned p = pp + (unsigned)u * pstride;
+        const float* v = vv[u];
+        const unsigned rem = p % HW;
+        const unsigned y = rem / (unsigned)W, x = rem - y * (unsigned)W;
+        const bool r0 = y == 0, rl = y == (unsigned)H - 1, q0 = x == 0, ql = x == (unsigned)W - 1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            acc[0][k] += v[k];
+            if (r0) acc[1][k] += v[k];
+            if (rl) acc[2][k] += v[k];
+            if (q0) acc[3][k] += v[k];
+            if (ql) acc[4][k] += v[k];
+        }
+        if ((r0 || rl) && (q0 || ql)) {          // a corner pixel (four per image): straight to memory
+            const int corner = (rl ? 2 : 0) + (ql ? 1 : 0);
+            if (r0 && rl) {                      // H == 1: the pixel is both a first-row and a last-row corner
+#pragma unroll
+                for (int k = 0; k < 8; ++k) atomicAdd(out + (size_t)(5 + (ql ? 1 : 0)) * C + c0 + k, (double)v[k]);
+            }
+            if (q0 && ql) {                      // W == 1
+#pragma unroll
+                for (int k = 0; k < 8; ++k) atomicAdd(out + (size_t)(5 + (rl ? 2 : 0)) * C + c0 + k, (double)v[k]);
+            }
+            if (r0 && rl && q0 && ql) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) atomicAdd(out + (size_t)5 * C + c0 + k, (double)v[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) atomicAdd(out + (size_t)(5 + corner) * C + c0 + k, (double)v[k]);
+        }
+      }
+    }
+    __shared__ float s_red[256][8 + 1];
+    const int t = threadIdx.x;
+    const int groups = C8 < 256 ? C8 : 256;
+    for (int q = 0; q < 5; ++q) {
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s_red[t][k] = acc[q][k];
+        __syncthreads();
+        for (int j = t; j < groups * 8; j += 256) {
+            const int g = j >> 3, k = j & 7;
+            double a = 0.0;
+            for (int u = g; u < 256; u += groups) a += (double)s_red[u][k];
+            const int c = (int)((blockIdx.x * 256u + (unsigned)g) % (unsigned)C8) * 8 + k;
+            atomicAdd(out + (size_t)q * C + c, a);
+        }
+    }
+}
+
+// part = double[5][Cout] = {count, sum over all output pixels of conv(x) + b, 0, 0, 0}: a partial like rrv_channel_stats'
+// (count and sum only), so that the ranks of a sharded pre-pass can merge it.
+__global__ void __launch_bounds__(256) conv_mean_finish_kernel(const double* __restrict__ sums, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, int Cin, int Cout, double count,
+                                                               double* __restrict__ part) {
+    extern __shared__ double s_tap[];           // [Cin][9]: sum of the input over the pixels tap t reads
+    for (int i = threadIdx.x; i < Cin * 9; i += 256) {
+        const int c = i / 9, t = i - c * 9, dy = t / 3, dx = t - dy * 3;
+        // pixels NOT read by tap (dy, dx): last row for dy = 0, first row for dy = 2; last / first column for dx = 0 / 2
+        const int row = dy == 0 ? 2 : (dy == 2 ? 1 : -1);          // index into sums of the excluded row (row H-1 / row 0)
+        const int col = dx == 0 ? 4 : (dx == 2 ? 3 : -1);          // excluded column (col W-1 / col 0)
+        double s = sums[c];
+        if (row >= 0) s -= sums[(size_t)row * Cin + c];
+        if (col >= 0) s -= sums[(size_t)col * Cin + c];
+        if (row >= 0 && col >= 0) s += sums[(size_t)(5 + (row == 2 ? 2 : 0) + (col == 4 ? 1 : 0)) * Cin + c];
+        s_tap[i] = s;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int o = blockIdx.x * 8 + warp; o < Cout; o += gridDim.x * 8) {      // one warp per output channel
+        double acc = 0.0;
+        const float* wo = w + (size_t)o * Cin * 9;
+        for (int i = lane; i < Cin * 9; i += 32) acc += (double)__ldg(wo + i) * s_tap[i];
+#pragma unroll
+        for (int k = 16; k > 0; k >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, k);
+        if (lane == 0) {
+            part[o] = count;
+            part[Cout + o] = acc + (bias ? (double)bias[o] * count : 0.0);
+            part[2 * Cout + o] = 0.0;
+            part[3 * Cout + o] = 0.0;
+            part[4 * Cout + o] = 0.0;
+        }
+    }
+}
+
+int conv3x3_output_sum(const void* in_hi, const void* in_lo, int N, int H, int W, int Cin, const float* w_oihw, const float* bias,
+                       int Cout, double* scratch, double* part, cudaStream_t st) {
+    RRV_REQUIRE(in_hi && w_oihw && scratch && part, "rrv_conv3x3_output_sum: NULL tensor");
+    RRV_REQUIRE(N > 0 && H > 0 && W > 0 && Cin % 8 == 0 && Cin / 8 <= 256 && 256 % (Cin / 8) == 0 && Cout > 0,
+                "rrv_conv3x3_output_sum: unsupported shape N=%d H=%d W=%d Cin=%d Cout=%d", N, H, W, Cin, Cout);
+    RRV_REQUIRE((long long)N * H * W < (1LL << 31), "rrv_conv3x3_output_sum: more than 2^31 pixels");
+    cudaMemsetAsync(scratch, 0, sizeof(double) * 9 * Cin, st);
+    const long long total = (long long)N * H * W * (Cin / 8);
+    const int grid = (int)std::min<long long>((total + 255) / 256, 148LL * 6);
+    border_sums_kernel<<<grid, 256, 0, st>>>((const uint16_t*)in_hi, (const uint16_t*)in_lo, N, H, W, Cin, scratch);
+    if (check_launch("border_sums_kernel")) return 1;
+    const size_t smem = sizeof(double) * 9 * (size_t)Cin;
+    RRV_REQUIRE(smem <= 48 * 1024, "rrv_conv3x3_output_sum: Cin=%d too large", Cin);
+    conv_mean_finish_kernel<<<(Cout + 7) / 8, 256, smem, st>>>(scratch, w_oihw, bias, Cin, Cout, (double)N * H * W, part);
+    return check_launch("conv_mean_finish_kernel");
+}
+
+}  // namespace rrv

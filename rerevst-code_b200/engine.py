@@ -316,6 +316,16 @@ class StyleEngine:
         L.check(self.lib.rrv_stats_merge(parts.data_ptr(), parts.shape[0], Cc, merged.data_ptr(), L.stream()), "rrv_stats_merge")
         return merged
 
+    def _pred_content_part(self, cw, x):
+        """Partial {count, sum} of conv3x3(x) + b over all output pixels WITHOUT running the convolution: FilterPredictor only
+        needs its mean (style_network_global.py:163-167), and that follows from nine border-aware channel sums of x
+        (rrv_conv3x3_output_sum).  Merged over the ranks of a sharded pre-pass like every other partial."""
+        scratch = torch.empty((9, cw.Cin), dtype=torch.float64, device=self.device)
+        part = torch.empty((5, cw.Cout), dtype=torch.float64, device=self.device)
+        L.check(self.lib.rrv_conv3x3_output_sum(L.ptr(x.hi), L.ptr(x.lo), x.N, x.H, x.W, cw.Cin, cw._keep.data_ptr(), L.ptr(cw.bias),
+                                                cw.Cout, scratch.data_ptr(), part.data_ptr(), L.stream()), "rrv_conv3x3_output_sum")
+        return self._merge_ranks(part)
+
     def _conv_stats(self, cw, x, ep, minmax, N=None):
         """fp32 NHWC convolution output + the finished partial statistics of that output (one pass on the tensor-core path)."""
         if not self.fused_stats or self._impl_for(cw) != L.IMPL_TCGEN05:
@@ -477,7 +487,7 @@ class StyleEngine:
         run as one 512 -> 64 convolution; spatial+batch mean; Linear(64 -> 1024) each."""
         fw = self.w[f]
         ep = make_epilogue(bias=fw["pred"].bias)
-        c_mean = self._finalize(self._conv_stats(fw["pred"], content, ep, False)[1], 2, 0.0)[0]
+        c_mean = self._finalize(self._pred_content_part(fw["pred"], content), 2, 0.0)[0]
         s = self._conv(fw["pred"], self.style["nstyle"], ep, L.OUT_F32_NHWC)
         part = torch.empty((5, 64), dtype=torch.float64, device=self.device)
         L.check(self.lib.rrv_channel_stats(s.data_ptr(), s.numel() // 64, 64, part.data_ptr(), L.stream()), "stats")
@@ -712,7 +722,7 @@ class StyleEngine:
             for j, f in enumerate(FILTERS):
                 fw = self.w[f]
                 ep = make_epilogue(bias=fw["pred"].bias)
-                c_mean = self._finalize(self._conv_stats(fw["pred"], h, ep, False)[1], 2, 0.0)[0]
+                c_mean = self._finalize(self._pred_content_part(fw["pred"], h), 2, 0.0)[0]
                 s_mean = self._style_pred_means(f)
                 wf = []
                 for q, (fcw, fcb) in enumerate(fw["fc"]):

@@ -1090,3 +1090,26 @@ def test_vgg19_loss_network_backward(L, dev, state_dict):
     lr.backward()
     assert abs(float(loss) - float(lr)) < 2e-3 * abs(float(lr))
     assert close(xd3.grad.cpu(), xr3.grad)
+
+
+@pytest.mark.parametrize("shape", [(2, 19, 32, 512, 64), (1, 1, 1, 64, 8), (3, 1, 7, 64, 16), (1, 6, 1, 128, 32), (1, 152, 256, 512, 64)])
+def test_conv3x3_output_sum_without_the_convolution(L, dev, shape):
+    """rrv_conv3x3_output_sum (FilterPredictor's mean of a convolution from nine border-aware sums of its input) against the
+    mean of the convolution itself, including 1-row / 1-column inputs where border rows and corners coincide."""
+    N, H, W, Cin, Cout = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(N, Cin, H, W, generator=g) + 0.25
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    xp = _to_planes(L, x.to(dev))
+    xq = _from_planes(L, xp).cpu().double()
+    ref = F.conv2d(xq, w.double(), b.double(), padding=1).sum(dim=(0, 2, 3))
+    wd, bd = w.to(dev).contiguous(), b.to(dev)
+    scratch = torch.empty((9, Cin), dtype=torch.float64, device=dev)
+    part = torch.empty((5, Cout), dtype=torch.float64, device=dev)
+    L.check(L.lib().rrv_conv3x3_output_sum(L.ptr(xp.hi), L.ptr(xp.lo), N, H, W, Cin, wd.data_ptr(), bd.data_ptr(), Cout, scratch.data_ptr(),
+                                           part.data_ptr(), L.stream()))
+    part = part.cpu()
+    assert torch.all(part[0] == N * H * W)
+    scale = float(F.conv2d(xq.abs(), w.double().abs(), b.double().abs(), padding=1).sum(dim=(0, 2, 3)).max())
+    assert float((part[1] - ref).abs().max()) < 1e-5 * scale
