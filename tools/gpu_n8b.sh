@@ -1,0 +1,10 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 tools/config4.py > gpurun_out/n8_config4.json 2> gpurun_out/n8_config4.err; echo "config4 n8 rc=$?"
+cat gpurun_out/n8_config4.json
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29543 tools/config4.py > gpurun_out/n8_config4_b.json 2> gpurun_out/n8_config4_b.err; echo "config4 n8 (2nd) rc=$?"
+cat gpurun_out/n8_config4_b.json
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/n4_bench.json 2> gpurun_out/n4_bench.err; echo "bench n4 rc=$?"
+timeout 600 python tools/config4.py --frames 256 > gpurun_out/n1_config3_clip.json 2> gpurun_out/n1_config3_clip.err; echo "clip256 n1 rc=$?"
+cat gpurun_out/n1_config3_clip.json
