@@ -689,9 +689,6 @@ struct Tc2Params {
     int ngrp[4][3];
     Grp grp[4][3][3];
     int tiles_x, tiles_y, n_ntiles, total_tiles;
-    int n_full;             // row-reuse loop with MT = 2: tiles [0, n_full) carry both M tiles; the tiles of the last, partial round
-                            // of the persistent schedule are split into their two halves (tile n_full + r/2, half r & 1), one per
-                            // worker, so that round costs half a tile time (n_full == total_tiles: no split)
     int BN, x3;             // BN = N of the MMA (3 Cout_pad when the dy taps are merged); x3: lo planes present
     int terms;              // MMAs per k-slice beyond hi*Whi: bit 0 = hi*Wlo, bit 1 = lo*Whi (3 = the full fp32-accurate split)
     int BNe;                // output channels per tile (= BN, or Cout_pad when merged)
@@ -711,26 +708,18 @@ struct Tc2Params {
     EpiDev ep;
 };
 
-// Tile index -> coordinates, identically in the producer, the MMA issuer and the epilogue.  mtc = M tiles this tile carries (an
-// MT = 2 tile whose second M tile lies entirely below the image, or a half tile of the split last round, carries one).
-// Returns false for a half tile with no row inside the image: every role skips it.
-__device__ __forceinline__ bool tile_coords(const Tc2Params& p, int tile, int xmul, int xoff, int cols, int rows, int& ph, int& n0,
+// Tile index -> coordinates, identically in the producer, the MMA issuer and the epilogue.  mtc = M tiles this tile carries: an
+// MT = 2 tile whose second M tile lies entirely below the image issues, loads and stores only the first one (304 rows = 9.5
+// tiles of 32: the last tile row of the 256-channel layers at 1080p).
+__device__ __forceinline__ void tile_coords(const Tc2Params& p, int tile, int xmul, int xoff, int cols, int rows, int& ph, int& n0,
                                             int& x0, int& y0, int& n, int& mtc) {
-    int t = tile, yadd = 0;
-    mtc = p.MT;
-    if (tile >= p.n_full) {
-        const int r = tile - p.n_full;
-        t = p.n_full + (r >> 1);
-        yadd = (r & 1) << 4;
-        mtc = 1;
-    }
+    int t = tile;
     ph = t % p.nph; t /= p.nph;
     n0 = (t % p.n_ntiles) * p.BNe; t /= p.n_ntiles;
     x0 = ((t % p.tiles_x) * xmul + xoff) * cols; t /= p.tiles_x;
-    y0 = (t % p.tiles_y) * rows + yadd;
+    y0 = (t % p.tiles_y) * rows;
     n = t / p.tiles_y;
-    if (mtc == 2 && y0 + 16 >= p.in_H) mtc = 1;
-    return y0 < p.in_H;
+    mtc = (p.MT == 2 && y0 + 16 >= p.in_H) ? 1 : p.MT;
 }
 
 // PAIR: two CTAs of a cluster issue one cta_group::2 MMA per k-slice (256 pixels x BN): each CTA loads its own A box
@@ -959,7 +948,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             bool first_set = true;
             for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
                 int ph, n0, x0, y0, n, mtc;
-                if (!tile_coords(p, tile, PAIR ? 2 : 1, (int)cta_rank, cols_per_tile, rows_per_set, ph, n0, x0, y0, n, mtc)) continue;
+                tile_coords(p, tile, PAIR ? 2 : 1, (int)cta_rank, cols_per_tile, rows_per_set, ph, n0, x0, y0, n, mtc);
                 const int by = y0 + p.a_y0[ph];
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     for (int j = 0; j < p.nA; ++j) {
@@ -1011,7 +1000,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         uint32_t pa = 0, pb = 0, aphase = 0;
         for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
             int ph, n0_, x0_, y0_, n_, mtc;
-            if (!tile_coords(p, tile, PAIR ? 2 : 1, 0, cols_per_tile, rows_per_set, ph, n0_, x0_, y0_, n_, mtc)) continue;
+            tile_coords(p, tile, PAIR ? 2 : 1, 0, cols_per_tile, rows_per_set, ph, n0_, x0_, y0_, n_, mtc);
             ptx::mbar_wait(ptx::smem_u32(&s_tempty[as]), aphase ^ 1u);
             ptx::tc_fence_after();
             const uint32_t d_set = tmem_base + (uint32_t)(as * p.set_stride);
@@ -1096,7 +1085,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         uint32_t aphase = 0;
         for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
             int ph, n0, x0, y0, n, mtc;
-            if (!tile_coords(p, tile, PAIR ? 2 : 1, (int)cta_rank, cols_per_tile, rows_per_set, ph, n0, x0, y0, n, mtc)) continue;
+            tile_coords(p, tile, PAIR ? 2 : 1, (int)cta_rank, cols_per_tile, rows_per_set, ph, n0, x0, y0, n, mtc);
             // (the full-chain and statistics instantiations never run the merged-phase layout: the host sends those to the generic one)
             constexpr bool kMode2 = DXM && FLAGS != (EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF) && FLAGS != EPI_HEAD;
             if (kMode2 && p.dxm == 2) {
@@ -1731,21 +1720,8 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         d.tiles_y = ceil_div(d.in_H, 16 * MT);
     }
     const long long total = (long long)d.N * d.tiles_y * d.tiles_x * d.n_ntiles * d.nph;
-    RRV_REQUIRE(total < (1LL << 30), "rrv_conv2d: too many tiles");
+    RRV_REQUIRE(total < (1LL << 31), "rrv_conv2d: too many tiles");
     d.total_tiles = (int)total;
-    d.n_full = d.total_tiles;
-    // Persistent schedule, tile t -> worker t % W: when the last round is at most half full, its tiles are split into their two M
-    // tiles so that the round costs half a tile time (256 -> 256 at 304 x 512: 320 tiles over 74 CTA pairs, 5 rounds -> 4.5;
-    // RRV_NO_TAIL_SPLIT=1 is the A/B switch)
-    static const bool no_split = getenv("RRV_NO_TAIL_SPLIT") != nullptr;
-    if (!no_split && !d.dxm && d.MT == 2) {
-        const int W = d.pair ? num_sms() / 2 : num_sms();
-        const int R = d.total_tiles % W;
-        if (d.total_tiles > W && R > 0 && 2 * R <= W) {
-            d.n_full = d.total_tiles - R;
-            d.total_tiles = d.n_full + 2 * R;
-        }
-    }
     d.ep = make_epi(p->ep, p->Cout);
     d.ep.lo_fp16 = 0;
     d.stats = p->stats;
