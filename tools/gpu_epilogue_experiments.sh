@@ -1,4 +1,7 @@
 #!/bin/bash
+# Bounding experiments for the epilogue of the merged-tap layers: build the measurement-only variants first
+#   tools/build_variants.sh nostore "-DRRV_EXP_NOSTORE=1" notab "-DRRV_EXP_NOTAB=1" noshfl "-DRRV_EXP_NOSHFL=1" all3 "-DRRV_EXP_NOSTORE=1 -DRRV_EXP_NOTAB=1 -DRRV_EXP_NOSHFL=1"
+# (their results are wrong by construction; profiles/r2_epilogue_bounding_experiments.txt)
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 D=rerevst-code_b200/csrc
