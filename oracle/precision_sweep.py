@@ -102,10 +102,17 @@ def main():
     ap.add_argument("--modes", default="x2a,x2w,h2w,h2a,bf16")
     ap.add_argument("--budget", type=float, default=5e-4)
     ap.add_argument("--cumulative", action="store_true")
+    ap.add_argument("--layers", default="", help="comma-separated prefixes of the layers to sweep (default: all)")
     args = ap.parse_args()
     torch.set_num_threads(os.cpu_count() or 1)
     sd = synthetic_state_dict(cases.WEIGHT_SEED)
-    style, samples, frame = cases.global_inputs(args.case)
+    if args.case == "full_1080p":          # the bench's frame size: 1216 x 2048 (1080p padded), pre-pass on two 270 x 480 samples
+        g = cases.gen()
+        style = torch.randn(1, 3, 256, 256, generator=g)
+        samples = [torch.randn(1, 3, 270, 480, generator=g) for _ in range(2)]
+        frame = torch.randn(1, 3, 1216, 2048, generator=g)
+    else:
+        style, samples, frame = cases.global_inputs(args.case)
     o = stylenet.GlobalOracle(sd)
     o.generate_style_features(style)
     o.clean()
@@ -120,7 +127,8 @@ def main():
     modes = args.modes.split(",")
     table = {}
     print("layer".ljust(18) + "".join(m.rjust(11) for m in modes))
-    for name in LAYERS:
+    sweep = [n for n in LAYERS if not args.layers or any(n.startswith(p) for p in args.layers.split(","))]
+    for name in sweep:
         row = []
         for m in modes:
             e = err(run(o, frame, {name: m}))
@@ -128,13 +136,13 @@ def main():
             row.append(e)
         print(name.ljust(18) + "".join(f"{e:11.2e}" for e in row), flush=True)
     for m in modes:
-        e = err(run(o, frame, {k: m for k in LAYERS}))
-        print(f"all layers {m}: {e:.3e}")
+        e = err(run(o, frame, {k: m for k in sweep}))
+        print(f"all swept layers {m}: {e:.3e}")
     if args.cumulative:
         for m in modes:
             if m == "bf16":
                 continue
-            order = sorted(LAYERS, key=lambda k: table[(k, m)])
+            order = sorted(sweep, key=lambda k: table[(k, m)])
             assign, kept = {}, []
             for name in order:
                 trial = dict(assign)
