@@ -283,6 +283,205 @@ __global__ void __launch_bounds__(256) first_layer_gray_kernel(const FirstDev p)
     }
 }
 
+// The same 9-tap gray convolution for the per-frame path (planes output, bf16 lo): persistent blocks whose WARPS work
+// independently.  Round-2 profile of the kernel above at 1216 x 2048 (profiles/r2_first_layer_before.txt): 183 us against an
+// 88 us floor (578 MB written at the 7.2 TB/s a memset reaches), 20.8 instructions per output of which 9.1 are the FFMAs --
+// per-pixel bound checks, 64-bit address arithmetic per store, block barriers per tile and the per-block table build made up
+// most of the rest.  Here:
+//   * unit of work = one image row x 32 columns, taken by ONE warp (lane = 8 pixels x 8 channels as above); the warp keeps its
+//     own 3 x 34 halo in shared memory (double-buffered, __syncwarp only): no block barrier after the prologue, so the store
+//     bursts of one warp overlap the arithmetic of the others;
+//   * grid = 2 blocks per SM, units dealt round-robin to the warps: the weight tables are built once per block;
+//   * interior units (every unit of a frame padded to a multiple of 32 except the border rows and the two border column
+//     groups) run without bound checks; one pointer per unit and plane, immediate offsets per pixel;
+//   * the next unit's uint8 pixels are fetched with cp.async into shared memory and only converted after this unit's stores
+//     (loaded into registers, the compiler converted them at once and a third of the issue slots waited for L2).
+// uint8 frames with W % 4 == 0 only (word-aligned rows); everything else takes the kernel above.
+template <bool LO>
+__global__ void __launch_bounds__(256, 2) first_layer_gray_rows_kernel(const FirstDev p, int units, int tiles_x) {
+    __shared__ __align__(16) float s_w1[9][64];
+    __shared__ __align__(16) float s_w0[9][64];
+    __shared__ float s_b[64];
+    __shared__ __align__(16) float s_h[8][2][3][40];      // [warp][buffer][row][column]: column 0 = x0 - 1, 34 used
+    __shared__ __align__(16) uint32_t s_raw[8][3][28];    // [warp][row]: the 27 aligned words that hold the row's 34 BGR pixels
+    const int tid = threadIdx.x;
+    const float mean[3] = {0.485f, 0.456f, 0.406f};
+    const float sd[3] = {0.229f, 0.224f, 0.225f};
+    for (int i = tid; i < 9 * 64; i += 256) {
+        const int co = i & 63, t = i >> 6;
+        float w1 = 0.0f, w0 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float w = p.w[co * 27 + c * 9 + t];
+            w1 = fmaf(w, GRAY_GS / sd[c], w1);
+            w0 = fmaf(w, (GRAY_GM - mean[c]) / sd[c], w0);
+        }
+        s_w1[t][co] = w1;
+        s_w0[t][co] = w0;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float b = p.bias[tid];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) b += s_w0[t][tid];
+        s_b[tid] = b;
+    }
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31;
+    const int q = lane & 7, c0 = (lane >> 3) * 8;
+    const int nw = gridDim.x * 8;
+    int u = blockIdx.x * 8 + warp;
+    if (u >= units) return;
+    float bq[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) bq[k] = s_b[q * 8 + k];
+    const uint8_t* src = (const uint8_t*)p.src;
+    const long long total = (long long)p.N * p.H * p.W * 3;
+
+    auto coords = [&](int unit, int& n_, int& oy_, int& ox0_) {
+        const int r = unit / tiles_x;
+        ox0_ = (unit - r * tiles_x) * FL_TW;
+        n_ = r / p.H;
+        oy_ = r - n_ * p.H;
+    };
+    // The uint8 pixels of a unit's halo travel global -> shared as aligned 32-bit words with cp.async (no registers, nothing
+    // waits for them until the unit before has been computed and stored); W % 4 == 0 keeps every row's first byte word-aligned.
+    auto fetch_raw = [&](int n_, int oy_, int ox0_) {
+        if (lane < 27) {
+            const int d = (3 * ox0_ + 1) & 3;                           // = 3 (x0 - 1) mod 4
+#pragma unroll
+            for (int rr = 0; rr < 3; ++rr) {
+                const int y = oy_ - 1 + rr;
+                const long long g = ((long long)n_ * p.H + y) * p.W * 3 + (3 * (ox0_ - 1) - d) + 4 * lane;
+                if (y >= 0 && y < p.H && g >= 0 && g + 4 <= total) {
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_raw[warp][rr][lane]);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src + g) : "memory");
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto convert_raw = [&](int oy_, int ox0_, int buf) {              // raw words -> centred gray values of the halo
+        const int d = (3 * ox0_ + 1) & 3;
+        const uint8_t* rb = reinterpret_cast<const uint8_t*>(&s_raw[warp][0][0]);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int rr = it < 3 ? it : (lane >> 1), c = it < 3 ? lane : FL_TW + (lane & 1);
+            if (it == 3 && lane >= 6) break;
+            const int y = oy_ - 1 + rr, x = ox0_ - 1 + c;
+            float uv = 0.0f;
+            if (y >= 0 && y < p.H && x >= 0 && x < p.W) {
+                const uint8_t* s3 = rb + rr * 112 + d + 3 * c;
+                const float g = fmaf(0.114f, (float)s3[2], fmaf(0.587f, (float)s3[1], 0.299f * (float)s3[0])) * (1.0f / 255.0f);
+                uv = (g - GRAY_GM) * (1.0f / GRAY_GS);
+            }
+            s_h[warp][buf][rr][c] = uv;
+        }
+    };
+    int n, oy, ox0;
+    coords(u, n, oy, ox0);
+    fetch_raw(n, oy, ox0);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    convert_raw(oy, ox0, 0);
+    __syncwarp();
+
+    for (int buf = 0;; buf ^= 1) {
+        const int u2 = u + nw;
+        const bool more = u2 < units;
+        int n2 = 0, oy2 = 0, ox2 = 0;
+        if (more) {                      // the next unit's pixels go in flight before this unit's arithmetic
+            coords(u2, n2, oy2, ox2);
+            fetch_raw(n2, oy2, ox2);
+        }
+        float acc[8][8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[j][k] = bq[k];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const float* hr = &s_h[warp][buf][dy][c0];
+            const float4 a0 = *reinterpret_cast<const float4*>(hr);
+            const float4 a1 = *reinterpret_cast<const float4*>(hr + 4);
+            const float2 a2 = *reinterpret_cast<const float2*>(hr + 8);
+            const float a[10] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y};
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                const float4* wp = reinterpret_cast<const float4*>(&s_w1[dy * 3 + dx][q * 8]);
+                const float4 wa = wp[0], wb = wp[1];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    acc[j][0] = fmaf(a[j + dx], wa.x, acc[j][0]);
+                    acc[j][1] = fmaf(a[j + dx], wa.y, acc[j][1]);
+                    acc[j][2] = fmaf(a[j + dx], wa.z, acc[j][2]);
+                    acc[j][3] = fmaf(a[j + dx], wa.w, acc[j][3]);
+                    acc[j][4] = fmaf(a[j + dx], wb.x, acc[j][4]);
+                    acc[j][5] = fmaf(a[j + dx], wb.y, acc[j][5]);
+                    acc[j][6] = fmaf(a[j + dx], wb.z, acc[j][6]);
+                    acc[j][7] = fmaf(a[j + dx], wb.w, acc[j][7]);
+                }
+            }
+        }
+        const int x0 = ox0 + c0;
+        const bool edge_row = oy == 0 || oy == p.H - 1;
+        if (edge_row || x0 == 0 || x0 + 8 >= p.W) {       // taps that fall outside the image carry no W0 term (border pixels only)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int ox = x0 + j;
+                if (ox < p.W && (edge_row || ox == 0 || ox == p.W - 1)) {
+#pragma unroll 1
+                    for (int tp = 0; tp < 9; ++tp) {
+                        const int y = oy + tp / 3 - 1, x = ox + tp % 3 - 1;
+                        if (y >= 0 && y < p.H && x >= 0 && x < p.W) continue;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) acc[j][k] -= s_w0[tp][q * 8 + k];
+                    }
+                }
+            }
+        }
+        const long long o = (((long long)n * p.H + oy) * p.W + x0) * 64 + q * 8;
+        uint16_t* ph = p.out_hi + o;
+        uint16_t* pl = LO ? p.out_lo + o : nullptr;
+        const int npx = min(8, p.W - x0);          // < 8 (or <= 0) only in the last, partial column tile
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (j >= npx) break;
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float v0 = fmaxf(acc[j][2 * i], 0.0f), v1 = fmaxf(acc[j][2 * i + 1], 0.0f);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+                hw[i] = *reinterpret_cast<const uint32_t*>(&h2);
+                if (LO) {
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(v0 - __uint_as_float(hw[i] << 16), v1 - __uint_as_float(hw[i] & 0xffff0000u));
+                    lw[i] = *reinterpret_cast<const uint32_t*>(&l2);
+                }
+            }
+            *reinterpret_cast<uint4*>(ph + j * 64) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            if (LO) *reinterpret_cast<uint4*>(pl + j * 64) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+        if (!more) break;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        convert_raw(oy2, ox2, buf ^ 1);  // s_h[buf ^ 1] was last read two units ago; a __syncwarp lies in between
+        __syncwarp();
+        u = u2; n = n2; oy = oy2; ox0 = ox2;
+    }
+}
+
+static int fl_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
 int first_layer(const void* src, int src_kind, int gray, int N, int H, int W, const float* w, const float* bias,
                 void* out_hi, void* out_lo, float* out_f32, cudaStream_t st) {
     RRV_REQUIRE(src && w && bias, "rrv_first_layer: NULL input");
@@ -291,6 +490,14 @@ int first_layer(const void* src, int src_kind, int gray, int N, int H, int W, co
     RRV_REQUIRE(out_hi || out_f32, "rrv_first_layer: no output requested");
     FirstDev d{src, w, bias, (uint16_t*)out_hi, (uint16_t*)out_lo, out_f32, N, H, W, src_kind, gray, g_lo_fp16};
     dim3 grid(ceil_div(W, FL_TW) * ceil_div(H, FL_TH), N);
+    if (gray && src_kind == 1 && out_hi && !out_f32 && !g_lo_fp16 && W % 4 == 0 && ((uintptr_t)src & 3) == 0 &&
+        (long long)N * H * ceil_div(W, FL_TW) < (1ll << 30)) {
+        const int tiles_x = ceil_div(W, FL_TW), units = N * H * tiles_x;
+        const int blocks = std::min(ceil_div(units, 8), 2 * fl_num_sms());
+        if (out_lo) first_layer_gray_rows_kernel<true><<<blocks, 256, 0, st>>>(d, units, tiles_x);
+        else first_layer_gray_rows_kernel<false><<<blocks, 256, 0, st>>>(d, units, tiles_x);
+        return check_launch("first_layer_gray_rows_kernel");
+    }
     if (gray) {
         dim3 ggrid(ceil_div(ceil_div(W, FL_TW), FL_TPB) * ceil_div(H, FL_TH), N);
         first_layer_gray_kernel<<<ggrid, 256, 0, st>>>(d);

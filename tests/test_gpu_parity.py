@@ -234,6 +234,42 @@ def test_first_layer_matches_oracle(L, dev, state_dict, kind, gray):
     assert rel_linf(out.permute(0, 3, 1, 2).cpu(), ref) < TIGHT
 
 
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("shape", [(2, 37, 52), (1, 8, 32), (1, 3, 100), (3, 40, 64), (1, 1, 4), (1, 9, 36), (2, 37, 53), (1, 300, 2048)])
+@pytest.mark.parametrize("with_lo", [True, False])
+def test_first_layer_gray_planes_kernel(L, dev, state_dict, kind, shape, with_lo):
+    """The per-frame instantiation (uint8 frame, gray, planes out, W % 4 == 0: first_layer_gray_rows_kernel, one image row x 32
+    columns per warp) against the fp32-output kernel and the oracle on ragged sizes: partial column tiles, border rows / columns,
+    fewer units than warps, more units than warps (300 x 2048); the other shapes / sources take the tile kernel."""
+    from oracle import stylenet
+    from rerevst_code_b200.engine import Planes
+    g = torch.Generator().manual_seed(7)
+    N, H, W = shape
+    w, b = state_dict["Encoder.slice.0.weight"], state_dict["Encoder.slice.0.bias"]
+    if kind == 0:
+        x = torch.randn(N, 3, H, W, generator=g)
+        src = x.to(dev)
+    else:
+        u8 = torch.randint(0, 256, (N, H, W, 3), generator=g, dtype=torch.uint8)
+        x = torch.cat([stylenet.transform_image(stylenet.numpy2tensor(u8[i].numpy())) for i in range(N)], 0)
+        src = u8.to(dev)
+    ref = F.relu(F.conv2d(stylenet.rgb2gray(x), w, b, padding=1))
+    wd, bd = w.to(dev), b.to(dev)
+    f32 = torch.empty((N, H, W, 64), dtype=torch.float32, device=dev)
+    L.check(L.lib().rrv_first_layer(src.data_ptr(), kind, 1, N, H, W, wd.data_ptr(), bd.data_ptr(), 0, 0, f32.data_ptr(), L.stream()))
+    o = Planes(N, H, W, 64, with_lo, dev)
+    o.hi.fill_(float("nan"))                            # every element must be written
+    if with_lo:
+        o.lo.fill_(0x7fc0)
+    L.check(L.lib().rrv_first_layer(src.data_ptr(), kind, 1, N, H, W, wd.data_ptr(), bd.data_ptr(), L.ptr(o.hi), L.ptr(o.lo), 0, L.stream()))
+    got = _from_planes(L, o)
+    assert torch.isfinite(got).all()
+    tol = 2.0 ** -16 if with_lo else 2.0 ** -8
+    scale = float(f32.abs().max()) + 1e-30
+    assert float((got.permute(0, 2, 3, 1) - f32).abs().max()) / scale < tol
+    assert rel_linf(got.cpu(), ref) < (TIGHT if with_lo else 5e-3)
+
+
 def test_maxpool_matches_torch(L, dev):
     from rerevst_code_b200.engine import Planes
     g = torch.Generator().manual_seed(2)
