@@ -122,6 +122,11 @@ int rrv_tc_tune_pair(int enable, int min_bn);
 /* Merge the three dx taps of a 3x3 convolution (and the column phases of a nearest-x2 one) into one MMA along N when
  * 3 (4) Cout <= 256: the 64-channel layers, whose cost is the A-operand fetch.  Enabled by default. */
 int rrv_tc_tune_merge(int enable);
+/* Programmatic dependent launch between consecutive convolutions of a stream (enabled by default): the next layer's CTAs are
+ * scheduled while the last persistent round of this one still runs, do their prologue and wait.  A caller that keeps several
+ * independent frames in flight on several streams turns it off while it captures their graphs: the waiting CTAs would hold exactly
+ * the SMs the other frame's kernels could use (1080p, 2 frames in flight: 173 frames/s with, 180 without). */
+int rrv_tc_tune_pdl(int enable);
 /* KernelFilter fold (apply_filter, style_network_global.py:194-217; per frame in test/style_network_frame.py:97-105): the two
  * predicted 32x32 matrices wf1, wf2 ([out][in], fp32) are multiplied into the filter's down_sample (512 -> 32) and upsample
  * (32 -> 512) 3x3 weights (PyTorch OIHW fp32) and written as tensor-core blobs: down_blob = rrv_tc_weight_bytes(512, 64, 3, 0)

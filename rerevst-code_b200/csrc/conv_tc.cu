@@ -81,6 +81,7 @@ struct TcTune {
     int dxm = 1;            // merge the three dx taps along N when 3 Cout_pad <= 256 (the 64-channel layers, the RGB head)
     int pair = 1;           // v2: CTA pairs (cta_group::2) for Cout tiles >= pair_min_bn
     int pair_min_bn = 64;   // (<= 64 also overrides resident weights: measured faster on the 64 -> 64 layers)
+    int pdl = 1;            // programmatic dependent launch: the next layer's CTAs start (and wait) while this layer's last round runs
 };
 TcTune g_tune;
 
@@ -1481,7 +1482,7 @@ int launch_tc2p(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, c
         attr[na].val.clusterDim.z = 1;
         ++na;
     }
-    if (!no_pdl) {
+    if (!no_pdl && g_tune.pdl) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
@@ -1819,6 +1820,11 @@ int tc_tune_pair(int enable, int min_bn) {
 
 int tc_tune_merge(int enable) {
     g_tune.dxm = enable ? 1 : 0;
+    return 0;
+}
+
+int tc_tune_pdl(int enable) {
+    g_tune.pdl = enable ? 1 : 0;
     return 0;
 }
 

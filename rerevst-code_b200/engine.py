@@ -127,7 +127,7 @@ def make_epilogue(bias=None, act=0, norm1=None, res=None, res_shift=0, res_broad
 class StyleEngine:
     """Everything ``TransformerNet`` needs on one GPU."""
 
-    MAX_PLANS = 3          # captured CUDA graphs kept (LRU by input shape)
+    MAX_PLANS = 6          # captured CUDA graphs kept (LRU by input shape, output kind and lane)
 
     def __init__(self, device, precision="x3", impl="auto"):
         self.device = torch.device(device)
@@ -637,13 +637,19 @@ class StyleEngine:
         return self._head(h, out, post)
 
     @torch.no_grad()
-    def forward_graphed(self, frame, kind=0, post=None):
+    def forward_graphed(self, frame, kind=0, post=None, lane=0):
         """forward() replayed from a CUDA graph: the ~30 launches of a frame (with their TMA descriptors baked
         in) are captured once per input shape and clip state, then each call is one D2D copy of the frame into
         the graph's static input plus one graph launch.  Returns the graph's static output tensor (valid until
-        the next call).  Any change of weights, style or clip statistics drops the captured graphs."""
+        the next call).  Any change of weights, style or clip statistics drops the captured graphs.
+
+        ``lane``: frames are independent, so a caller may keep two of them in flight on two streams (lane_streams()): each
+        lane owns its graph, static input / output and activation pool.  Every layer's persistent grid ends with a partly
+        filled last round (conv4_1: 160 tiles on 74 CTA pairs = 3 rounds for 2.05 rounds of work) and a launch gap; the other
+        lane's kernels fill those SMs."""
         self._require_ready()
-        key = ("graph", kind, tuple(frame.shape), frame.dtype, post)
+        pdl = self.__dict__.get("_lanes", 1) == 1      # several frames in flight: no early launch of the next layer (rrv_tc_tune_pdl)
+        key = ("graph", kind, tuple(frame.shape), frame.dtype, post, lane, pdl)
         plan = self._plans.get(key)
         if plan is None:
             if kind == 0:
@@ -663,8 +669,12 @@ class StyleEngine:
             launches = self.lib.rrv_launch_count() - n0
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                self.forward(g_in, kind, out=g_out, post=post)
+            L.check(self.lib.rrv_tc_tune_pdl(1 if pdl else 0), "rrv_tc_tune_pdl")       # baked into the captured launches
+            try:
+                with torch.cuda.graph(graph):
+                    self.forward(g_in, kind, out=g_out, post=post)
+            finally:
+                self.lib.rrv_tc_tune_pdl(1)
             plan = (graph, g_in, g_out, launches)
             self._plans[key] = plan
             while len(self._plans) > self.MAX_PLANS:        # each plan pins a private pool with a frame's activations
@@ -676,6 +686,18 @@ class StyleEngine:
         graph.replay()
         self.graph_launches += launches
         return g_out
+
+    def lane_streams(self, n):
+        """Streams for ``n`` frames in flight: [the current stream, side streams ...] (forward_graphed(..., lane=i) is called with
+        stream i current).  The side streams first wait for everything queued on the current stream."""
+        cur = torch.cuda.current_stream(self.device)
+        self._lanes = max(1, int(n))
+        side = self.__dict__.setdefault("_lane_side", [])
+        while len(side) < n - 1:
+            side.append(torch.cuda.Stream(self.device))
+        for st in side[:n - 1]:
+            st.wait_stream(cur)
+        return [cur] + side[:n - 1]
 
     # ------------------------------------------------------------------ frame mode (use_Global=False) and training-side VGG
     def _frame_norm(self, x_f32):

@@ -86,7 +86,7 @@ class Stylization:
         upsamples), e.g. 436 x 1024 -> 432 x 1024 exactly like the reference."""
         return (H // 8) * 8, (W // 8) * 8
 
-    def transfer_stream(self, frames, crop=None, depth=3, pad_to=None, copy=True, out_dtype="f32"):
+    def transfer_stream(self, frames, crop=None, depth=4, pad_to=None, copy=True, out_dtype="f32", lanes=None):
         """Generator over an iterable of uint8 BGR frames of one size: yields exactly what
         ``transfer(frame, crop)`` returns for each, in order, but pipelined -- the pinned-memory
         upload of frame i+1 (copy-in stream) and the download of frame i-1 (copy-out stream) overlap the
@@ -99,12 +99,21 @@ class Stylization:
         ``pad_to=(PH, PW)``: the frames are RAW; ReshapeTool.process (generate_real_video.py:66-83, reflect border of 64
         pixels up to PH x PW) runs on the device, and ``crop`` defaults to the raw frame's window (:167).
 
-        ``out_dtype="u8"``: uint8 frames (see transfer): 6.2 MB instead of 24.9 MB per 1080p frame over PCIe."""
+        ``out_dtype="u8"``: uint8 frames (see transfer): 6.2 MB instead of 24.9 MB per 1080p frame over PCIe.
+
+        ``lanes``: frames whose kernels run concurrently (default 2 in global mode, where a frame is one graph replay without
+        shared scratch; 1 in frame mode): consecutive frames alternate between two compute streams, so that the SMs one
+        frame's layer leaves idle in its last persistent round run the other frame's kernels (engine.forward_graphed)."""
         if out_dtype not in ("f32", "u8"):
             raise ValueError("out_dtype must be 'f32' or 'u8'")
         t_out = torch.uint8 if out_dtype == "u8" else torch.float32
         eng = self.model._eng()
-        cur = torch.cuda.current_stream(self.device)
+        if lanes is None:
+            lanes = 2 if self.use_Global else 1
+        if lanes < 1 or (lanes > 1 and not self.use_Global):
+            raise ValueError("lanes must be >= 1 (and 1 in frame mode)")
+        depth = max(depth, lanes + 1)
+        comp = eng.lane_streams(lanes)
         s_in, s_out = self._side_streams()
         slots, pending = [], []
 
@@ -147,18 +156,21 @@ class Stylization:
                 s_in.wait_event(slot["ev_free"])            # the kernels that read dev_in last time are done
                 slot["dev_in"].copy_(slot["host_in"], non_blocking=True)
                 slot["ev_in"].record(s_in)
-            cur.wait_event(slot["ev_in"])
-            net_in = slot["dev_in"]
-            if pad_to is not None:
-                net_in = slot["dev_pad"]
-                L.check(L.lib().rrv_reflect_pad_u8(slot["dev_in"].data_ptr(), 1, rH, rW, 64, 64, H, W, net_in.data_ptr(), L.stream()),
-                        "rrv_reflect_pad_u8")
-            cur.wait_event(slot["ev_out"])                  # dev_out of this slot has been downloaded
-            # the network's output is the captured graph's single static buffer: a device-to-device copy (~10 us at 1080p) into
-            # this slot's buffer lets the next frame's kernels start while this frame is still being downloaded
-            slot["dev_out"].copy_(self._net(eng, net_in, (out_dtype, (y0, x0, h, w))), non_blocking=True)
-            slot["ev_free"].record(cur)
-            slot["ev_done"].record(cur)
+            lane = i % lanes
+            cur = comp[lane]
+            with torch.cuda.stream(cur):
+                cur.wait_event(slot["ev_in"])
+                net_in = slot["dev_in"]
+                if pad_to is not None:
+                    net_in = slot["dev_pad"]
+                    L.check(L.lib().rrv_reflect_pad_u8(slot["dev_in"].data_ptr(), 1, rH, rW, 64, 64, H, W, net_in.data_ptr(), L.stream()),
+                            "rrv_reflect_pad_u8")
+                cur.wait_event(slot["ev_out"])                  # dev_out of this slot has been downloaded
+                # the network's output is the lane's captured graph's static buffer: a device-to-device copy (~10 us at 1080p) into
+                # this slot's buffer lets the lane's next frame start while this frame is still being downloaded
+                slot["dev_out"].copy_(self._net(eng, net_in, (out_dtype, (y0, x0, h, w)), lane), non_blocking=True)
+                slot["ev_free"].record(cur)
+                slot["ev_done"].record(cur)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(slot["ev_done"])
                 slot["host_out"].copy_(slot["dev_out"], non_blocking=True)
@@ -167,12 +179,12 @@ class Stylization:
         while pending:
             yield finish(pending.pop(0))
 
-    def _net(self, eng, dev_u8, post):
+    def _net(self, eng, dev_u8, post, lane=0):
         """uint8 NHWC frame on the device -> the finished [N, h, w, 3] BGR frame on the device.  Global mode: one CUDA-graph
         replay whose last kernel (the RGB head) also de-normalises, clamps, crops and converts; the returned tensor is the
         graph's static output, valid until the next call."""
         if self.use_Global:
-            return eng.forward_graphed(dev_u8, kind=1, post=post)
+            return eng.forward_graphed(dev_u8, kind=1, post=post, lane=lane)
         y = eng.forward_frame_graphed(dev_u8, kind=1, gray=True)
         return eng.postprocess(y, post[1], post[0])
 

@@ -46,6 +46,7 @@ def _reset_kernel_tuning():
         lib.rrv_tc_tune(256, 2)
         lib.rrv_tc_tune_pair(1, 64)
         lib.rrv_tc_tune_merge(1)
+        lib.rrv_tc_tune_pdl(1)
         lib.rrv_set_lo_format(0)
     except Exception:
         pass

@@ -707,6 +707,12 @@ def test_transfer_stream_equals_transfer(L, dev, state_dict):
         assert np.array_equal(a, b)
     for i, a in enumerate(fw.transfer_stream(iter(frames), crop=crop, depth=2, copy=False)):     # zero-copy: valid until the next item
         assert np.array_equal(a, want[i])
+    for lanes in (1, 2, 3):              # frames in flight on separate compute streams: same frames, same order
+        for out_dtype in ("f32", "u8"):
+            got = list(fw.transfer_stream(iter(frames), crop=crop, lanes=lanes, out_dtype=out_dtype))
+            assert len(got) == len(want)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b if out_dtype == "f32" else np.rint(b).astype(np.uint8)), (lanes, out_dtype)
     # pad_to: raw frames, reflect border on the device, cropped back to the raw window (generate_real_video.py:66-83, :167)
     raw = [smooth(40, 56) for _ in range(4)]
     padded = [np.pad(f, ((64, 192 - 64 - 40), (64, 192 - 64 - 56), (0, 0)), mode="symmetric") for f in raw]
@@ -714,6 +720,33 @@ def test_transfer_stream_equals_transfer(L, dev, state_dict):
     got = list(fw.transfer_stream(iter(raw), pad_to=(192, 192)))
     for a, b in zip(got, want):
         assert a.shape == (40, 56, 3) and np.array_equal(a, b)
+
+
+def test_forward_graphed_lanes_run_concurrently_and_agree(L, dev, state_dict):
+    """Two frames in flight (engine.forward_graphed(..., lane=i) on engine.lane_streams()): every lane returns bit for bit what
+    a single lane returns, whatever the interleaving on the device."""
+    from rerevst_code_b200.framework import Stylization
+    g = torch.Generator().manual_seed(3)
+    fw = Stylization(state_dict, cuda=True)
+    fw.prepare_style(torch.randint(0, 256, (64, 64, 3), generator=g, dtype=torch.uint8).numpy())
+    fw.clean()
+    fw.add(torch.randint(0, 256, (48, 64, 3), generator=g, dtype=torch.uint8).numpy())
+    fw.compute()
+    eng = fw.model._eng()
+    frames = [torch.randint(0, 256, (1, 192, 256, 3), generator=g, dtype=torch.uint8).to(dev) for _ in range(6)]
+    post = ("u8", (8, 8, 160, 200))
+    want = [eng.forward_graphed(f, kind=1, post=post).clone() for f in frames]
+    streams = eng.lane_streams(2)
+    outs = [None] * len(frames)
+    for rep in range(3):
+        for i, f in enumerate(frames):
+            with torch.cuda.stream(streams[i % 2]):
+                outs[i] = eng.forward_graphed(f, kind=1, post=post, lane=i % 2).clone()
+        for st in streams[1:]:
+            streams[0].wait_stream(st)
+        torch.cuda.synchronize()
+        for a, b in zip(outs, want):
+            assert torch.equal(a, b)
 
 
 def test_generate_real_video_entry(tmp_path, dev, state_dict):
