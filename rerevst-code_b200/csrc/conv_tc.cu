@@ -38,11 +38,17 @@
 #ifndef RRV_EPI_PREFETCH
 #define RRV_EPI_PREFETCH 2      // before waiting for the accumulators: 1 = load the first chunk's residual into registers
 #endif                          // (spills at 168 registers), 2 = prefetch its cache lines into L1 (no registers)
+#ifndef RRV_EPI_PREFETCH_RR
+#define RRV_EPI_PREFETCH_RR RRV_EPI_PREFETCH    // the same choice for the row-reuse (not merged-tap) instantiations
+#endif
 #ifndef RRV_EPI_HALF16
 #define RRV_EPI_HALF16 1        // merged-tap epilogue: combine the three taps 16 columns at a time (register pressure)
 #endif
 #ifndef RRV_EPI_RESVOL
 #define RRV_EPI_RESVOL 1        // residual loads as volatile asm at the top of the chunk
+#endif
+#ifndef RRV_EPI_L2PF
+#define RRV_EPI_L2PF 1          // epilogue warps prefetch the NEXT tile's residual lines into L2 (bit 0: row-reuse layers, bit 1: merged-tap layers)
 #endif
 #ifndef RRV_EPI_FOLD
 #define RRV_EPI_FOLD 1          // norm stages as one FMA + clamps with pre-multiplied constants
@@ -1087,6 +1093,39 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
             int ph, n0, x0, y0, n, mtc;
             tile_coords(p, tile, PAIR ? 2 : 1, (int)cta_rank, cols_per_tile, rows_per_set, ph, n0, x0, y0, n, mtc);
+#if RRV_EPI_L2PF
+            // The residual of a tile is first touched by this kernel (it comes from DRAM): ask L2 for the NEXT tile's lines now, a
+            // whole tile time before the loads that need them (ncu: 57 % of the epilogue warps' stall samples of the KernelFilter
+            // up-convolutions were long-scoreboard waits on exactly those loads).  One 128-byte line per plane and lane; the two warps
+            // of a TMEM quadrant alternate lines.
+            {
+                constexpr bool kResS = FLAGS >= 0 && (FLAGS & EPI_RES) != 0;
+                const bool res_any = FLAGS >= 0 ? kResS : e.res_hi != nullptr;
+                const bool want = DXM ? (RRV_EPI_L2PF & 2) != 0 : (RRV_EPI_L2PF & 1) != 0;
+                if (want && res_any && tile + n_workers < p.total_tiles) {
+                    int ph2, n02, x02, y02, n2, mtc2;
+                    tile_coords(p, tile + n_workers, PAIR ? 2 : 1, (int)cta_rank, cols_per_tile, rows_per_set, ph2, n02, x02, y02, n2, mtc2);
+                    const int esz = e.res_f32 ? 4 : 2;
+                    const int lines = (p.BNe * esz) >> 7;             // whole lines inside the pixel's channel range only
+                    for (int mt = 0; mt < mtc2; ++mt) {
+                        const int iy = y02 + (DXM ? 0 : 16 * mt) + ty, ix = x02 + tx;
+                        bool v2 = iy < p.in_H && ix < p.in_W && (!DXM || tx < 30);
+                        const int oy = p.nph == 4 ? 2 * iy + (ph2 >> 1) : iy;
+                        const int ox = p.nph == 4 ? 2 * ix + (ph2 & 1) : ix;
+                        if (e.res_shift) v2 = v2 && ((oy | ox) & 1) == 0;      // one lane per shared low-resolution pixel
+                        if (!v2) continue;
+                        const long long off = ((long long)n2 * e.res_batch_stride +
+                                               ((long long)(oy >> e.res_shift) * e.res_W + (ox >> e.res_shift)) * e.C + n02) * esz;
+                        const char* bh = reinterpret_cast<const char*>(e.res_hi) + off;
+                        const char* bl = e.res_lo ? reinterpret_cast<const char*>(e.res_lo) + off : nullptr;
+                        for (int l = half; l < lines; l += 2) {
+                            ptx::prefetch_l2(bh + l * 128);
+                            if (bl) ptx::prefetch_l2(bl + l * 128);
+                        }
+                    }
+                }
+            }
+#endif
             // (the full-chain and statistics instantiations never run the merged-phase layout: the host sends those to the generic one)
             constexpr bool kMode2 = DXM && FLAGS != (EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF) && FLAGS != EPI_HEAD;
             if (kMode2 && p.dxm == 2) {
@@ -1184,7 +1223,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const bool has_res = FLAGS >= 0 ? kHasResStatic : e.res_hi != nullptr;
             uint4 pre_rh[CW / 8], pre_rl[CW / 8];
             bool pre = false;
-            if (RRV_EPI_PREFETCH && has_res && !RRV_EXP_NORES) {
+            constexpr int kPrefetch = DXM ? RRV_EPI_PREFETCH : RRV_EPI_PREFETCH_RR;
+            if (kPrefetch && has_res && !RRV_EXP_NORES) {
                 const int iy = y0 + ty, ix = x0 + tx;
                 const bool valid = iy < p.in_H && ix < p.in_W && (!DXM || tx < 30);
                 const int oy = p.nph == 4 ? 2 * iy + (ph >> 1) : iy;
@@ -1192,7 +1232,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 const PixCtx px = make_pix(p.o, e, n, oy, ox, valid);
                 const int cb = n0 + half * CW;
                 const bool can = half < nchunks && cb + CW <= p.o.Cout && half * CW + CW <= p.BNe;      // warp-uniform
-                if (RRV_EPI_PREFETCH == 1 && !e.res_f32) {
+                if (kPrefetch == 1 && !e.res_f32) {
                     pre = can;
                     if (pre && valid) {
 #pragma unroll

@@ -17,10 +17,13 @@ LAYERS = {  # name: (H, W, Cin, Cout, k, ups)
     "c64_512": (152, 256, 64, 512, 3, 0), "u512_256": (304, 512, 512, 256, 3, 1), "u256_128": (608, 1024, 256, 128, 3, 1),
     "u128_64": (1216, 2048, 128, 64, 3, 1), "s128_64": (608, 1024, 128, 64, 1, 0), "head": (1216, 2048, 64, 3, 3, 0),
     "s512_256": (152, 256, 512, 256, 1, 0), "s256_128": (304, 512, 256, 128, 1, 0),
+    "kfup": (152, 256, 64, 512, 3, 0), "kfup3": (152, 256, 64, 512, 3, 0),
 }
 
 
 FULL = "--full" in sys.argv
+KF = "--kf" in sys.argv        # the KernelFilter up-convolution as the frame runs it: 32 real input channels of 64, + residual planes
+                               # (kfup), + Decoder.norm[1] and AdaIN (kfup3)
 
 
 def bench(name, tunings, iters=5):
@@ -37,7 +40,18 @@ def bench(name, tunings, iters=5):
     d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = 1, H, W, Cin, Cout, k, ups
     d.in_hi, d.in_lo = L.ptr(xp.hi), L.ptr(xp.lo)
     d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
-    if FULL and Cout % 8 == 0:      # ResidualBlock.conv2 epilogue: norm1, + half-res shortcut, norm2, AdaIN
+    if KF:
+        d.Cin_used = 32
+        res = Planes(1, H, W, Cout, True, dev)
+        res.hi.normal_()
+        res.lo.zero_()
+        if name.endswith("3"):
+            tab = torch.stack([torch.zeros(Cout), torch.ones(Cout), torch.full((Cout,), -3.0), torch.full((Cout,), 3.0)]).to(dev).contiguous()
+            aff = torch.stack([torch.ones(Cout), torch.zeros(Cout)]).to(dev).contiguous()
+            d.ep = make_epilogue(bias=cw.bias, res=res, norm2=tab, affine=aff)
+        else:
+            d.ep = make_epilogue(bias=cw.bias, res=res)
+    elif FULL and Cout % 8 == 0:      # ResidualBlock.conv2 epilogue: norm1, + half-res shortcut, norm2, AdaIN
         tab = torch.stack([torch.zeros(Cout), torch.ones(Cout), torch.full((Cout,), -3.0), torch.full((Cout,), 3.0)]).to(dev).contiguous()
         aff = torch.stack([torch.ones(Cout), torch.zeros(Cout)]).to(dev).contiguous()
         res = Planes(1, H // 2, W // 2, Cout, True, dev)
@@ -72,6 +86,10 @@ def bench(name, tunings, iters=5):
 
 
 if __name__ == "__main__":
+    if "--one" in sys.argv:      # the shipped tuning only (A/B of library builds: RRV_LIB_PATH)
+        for n in [a for a in sys.argv[1:] if not a.startswith("--")]:
+            bench(n, {"default": (2, 1, 64, 256)}, iters=50)
+        sys.exit(0)
     if "--small" in sys.argv:
         T = {"default": (2, 1, 64, 256), "mt1": (1, 1, 64, 256), "bn128": (2, 1, 64, 128), "mt1_bn128": (1, 1, 64, 128),
              "mt1_bn64": (1, 1, 64, 64)}
