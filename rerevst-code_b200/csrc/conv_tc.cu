@@ -580,6 +580,70 @@ __device__ __forceinline__ void epilogue_chunk(const OutDesc& o, const EpiDev& e
     }
 }
 
+// Row-reuse layers whose epilogue is exposed (few MMAs per output value: the KernelFilter up-convolutions, conv2_1): a lane is a
+// pixel, so its 16-byte loads / stores of a 512-channel tensor land in 32 different lines per instruction and the LSU, not the
+// arithmetic, sets the pace (ncu: the epilogue warps wait on residual loads for 57 % of their samples, then on the load / store
+// queue).  Here a warp's chunk -- 4 rows x 8 columns x 32 channels, 64 bytes per pixel and plane -- lives in one of two staging
+// buffers (rows of 64 bytes, SWIZZLE_64B):
+//   * the residual planes of the NEXT chunk are copied in by cp.async with a transposed lane map (four lanes cover one pixel's 64
+//     bytes: 8 lines per instruction instead of 32) while this chunk is processed;
+//   * the chain runs in place (each lane reads and rewrites its own row);
+//   * the elected lane writes the finished rows with one TMA store per plane (box 32 channels x 8 x 4 pixels).
+struct RrNext {                 // where the next chunk's residual comes from (per lane: column lane >> 2, 16-byte piece lane & 3)
+    const uint16_t* hi;
+    const uint16_t* lo;
+    long long row_stride;       // elements between image rows
+    int rows;                   // rows of the 4 that lie inside the image; 0: nothing to fetch
+};
+
+__device__ __forceinline__ uint32_t rr_piece_off(int row, int piece) { return (uint32_t)(row * 64 + ((piece ^ ((row >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ void rr_fetch(const RrNext& nx, uint32_t buf_hi, uint32_t buf_lo, int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (i < nx.rows) {
+            const uint32_t off = rr_piece_off(8 * i + (lane >> 2), lane & 3);
+            ptx::cp_async16(buf_hi + off, nx.hi + i * nx.row_stride);
+            if (nx.lo) ptx::cp_async16(buf_lo + off, nx.lo + i * nx.row_stride);
+        }
+    }
+}
+
+template <int FLAGS>
+__device__ __forceinline__ void epilogue_chunk_rr(const OutDesc& o, const EpiDev& e, const float* s_tab, int ts, uint32_t taddr,
+                                                  const PixCtx& px, int cb, uint32_t buf_hi, uint32_t buf_lo, bool rs, const RrNext& nx,
+                                                  uint32_t nbuf_hi, uint32_t nbuf_lo, int lane) {
+    uint32_t r[CW];
+    ptx::tmem_ld32_issue(taddr, r);
+    ptx::tmem_ld32_wait(r);
+    // the other buffer was the source of the TMA store issued one chunk ago: it has been read by now
+    if (lane == 0) ptx::bulk_wait_read0();
+    __syncwarp();
+    if (rs) {
+        rr_fetch(nx, nbuf_hi, nbuf_lo, lane);
+        ptx::cp_async_commit();
+        ptx::cp_async_wait1();             // this chunk's residual (committed one chunk ago) has landed
+        __syncwarp();
+    }
+#pragma unroll
+    for (int g = 0; g < CW / 8; ++g) {
+        const uint32_t off = rr_piece_off(lane, g);
+        uint4 rh = make_uint4(0, 0, 0, 0), rl = make_uint4(0, 0, 0, 0);
+        if (rs) {
+            rh = ptx::lds_v4(buf_hi + off);
+            if (e.res_lo) rl = ptx::lds_v4(buf_lo + off);
+        }
+        float x[8];
+        chain8<FLAGS>(e, s_tab, ts, cb + g * 8, r + g * 8, x, rh, rl, true, px, o.Cout);
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        if (px.valid) {
+            ptx::sts_v4(buf_hi + off, hi);
+            if (o.out_lo) ptx::sts_v4(buf_lo + off, lo);
+        }
+    }
+}
+
 // Pooled variant (Encoder conv1_2 / conv2_2 / conv3_4, whose only consumer is the 2x2 max-pool): the pool runs on
 // the raw accumulators -- bias + ReLU are monotonic, so they commute with the max -- and only the pooled pixel goes
 // through the chain and to memory (a quarter of the stores; the full-resolution tensor never exists).
@@ -710,8 +774,10 @@ struct Tc2Params {
     int acc_stride, set_stride, bufs, tmem_cols;
     double* stats;          // rrv_conv.stats: double[5][Cout] accumulated by the epilogue (EPI_STATS instantiations), or NULL
     int stats_minmax;
-    int ostage;             // merged-tap layers with planes output: bytes of per-warp output staging per plane (2048 | 4096), 0 = direct stores
-    int ostage_off;         // offset of the staging area (EPI_WARPS x 2 planes x ostage bytes) in dynamic shared memory
+    int ostage;             // planes output through per-warp staging rows + TMA stores: bytes per plane and buffer (2048), 0 = direct stores
+    int ostage_off;         // offset of the staging area (EPI_WARPS x ostage_bufs x 2 planes x ostage bytes) in dynamic shared memory
+    int ostage_bufs;        // 1 (merged-tap layers), 2 (row-reuse layers: epilogue_chunk_rr alternates them)
+    int rstage;             // row-reuse layers: the residual planes arrive in the staging rows too (cp.async, one chunk ahead)
     EpiDev ep;
 };
 
@@ -1079,7 +1145,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         // the full-chain and norm1-only merged-tap instantiations (slice2.conv2, slice2.conv1) always store through the staging rows
         constexpr bool kStaged = DXM && (FLAGS == (EPI_N1 | EPI_RES | EPI_N2 | EPI_AFF) || FLAGS == EPI_N1);
         // this warp's output staging rows (hi plane, then lo plane), 1024-byte aligned
-        const uint32_t o_stage = p.ostage ? smem_base + (uint32_t)p.ostage_off + (uint32_t)((warp - 2) * 2 * p.ostage) : 0u;
+        const uint32_t o_stage = p.ostage ? smem_base + (uint32_t)p.ostage_off + (uint32_t)((warp - 2) * 2 * p.ostage_bufs * p.ostage) : 0u;
         constexpr bool STATS = FLAGS >= 0 && (FLAGS & EPI_STATS) != 0;
         StatAcc sacc;
         if (STATS) {
@@ -1090,6 +1156,30 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         int st_n0 = 0;
         int as = 0;
         uint32_t aphase = 0;
+        // staged row-reuse epilogue (epilogue_chunk_rr): where a chunk's residual comes from, per lane
+        constexpr bool kRR = !DXM && (FLAGS == 0 || FLAGS == EPI_RES || FLAGS == (EPI_RES | EPI_N2 | EPI_AFF));
+        const bool rr = kRR && p.ostage != 0;
+        const bool rr_rs = rr && p.rstage != 0;
+        int rr_par = 0;
+        auto rr_next_of = [&](int tile_, int mt_, int ch_) {
+            RrNext nx;
+            nx.hi = nullptr; nx.lo = nullptr; nx.row_stride = 0; nx.rows = 0;
+            if (!rr_rs || tile_ >= p.total_tiles) return nx;
+            int ph_, n0_, x0_, y0_, n_, mtc_;
+            tile_coords(p, tile_, PAIR ? 2 : 1, (int)cta_rank, cols_per_tile, rows_per_set, ph_, n0_, x0_, y0_, n_, mtc_);
+            const int yq = y0_ + 16 * mt_ + quad * 4, xc = x0_ + (lane >> 2);
+            if (xc >= p.in_W || yq >= p.in_H) return nx;
+            nx.rows = p.in_H - yq < 4 ? p.in_H - yq : 4;
+            nx.row_stride = (long long)e.res_W * e.C;
+            const long long off = (long long)n_ * e.res_batch_stride + ((long long)yq * e.res_W + xc) * e.C + n0_ + ch_ * CW + (lane & 3) * 8;
+            nx.hi = e.res_hi + off;
+            nx.lo = e.res_lo ? e.res_lo + off : nullptr;
+            return nx;
+        };
+        if (rr_rs) {                                  // the first chunk's residual
+            if (half < nchunks) rr_fetch(rr_next_of(cta_id, 0, half), o_stage, o_stage + (uint32_t)p.ostage, lane);
+            ptx::cp_async_commit();
+        }
         for (int tile = cta_id; tile < p.total_tiles; tile += n_workers) {
             int ph, n0, x0, y0, n, mtc;
             tile_coords(p, tile, PAIR ? 2 : 1, (int)cta_rank, cols_per_tile, rows_per_set, ph, n0, x0, y0, n, mtc);
@@ -1102,7 +1192,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 constexpr bool kResS = FLAGS >= 0 && (FLAGS & EPI_RES) != 0;
                 const bool res_any = FLAGS >= 0 ? kResS : e.res_hi != nullptr;
                 const bool want = DXM ? (RRV_EPI_L2PF & 2) != 0 : (RRV_EPI_L2PF & 1) != 0;
-                if (want && res_any && tile + n_workers < p.total_tiles) {
+                if (want && res_any && !rr_rs && tile + n_workers < p.total_tiles) {
                     int ph2, n02, x02, y02, n2, mtc2;
                     tile_coords(p, tile + n_workers, PAIR ? 2 : 1, (int)cta_rank, cols_per_tile, rows_per_set, ph2, n02, x02, y02, n2, mtc2);
                     const int esz = e.res_f32 ? 4 : 2;
@@ -1224,7 +1314,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             uint4 pre_rh[CW / 8], pre_rl[CW / 8];
             bool pre = false;
             constexpr int kPrefetch = DXM ? RRV_EPI_PREFETCH : RRV_EPI_PREFETCH_RR;
-            if (kPrefetch && has_res && !RRV_EXP_NORES) {
+            if (kPrefetch && has_res && !RRV_EXP_NORES && !rr_rs) {
                 const int iy = y0 + ty, ix = x0 + tx;
                 const bool valid = iy < p.in_H && ix < p.in_W && (!DXM || tx < 30);
                 const int oy = p.nph == 4 ? 2 * iy + (ph >> 1) : iy;
@@ -1306,6 +1396,27 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         ptx::tma_store_4d(&map_o_hi, o_stage, half * CW, x0, iy, n);
                         if (p.o.out_lo) ptx::tma_store_4d(&map_o_lo, o_stage + (uint32_t)p.ostage, half * CW, x0, iy, n);
                         ptx::bulk_commit();
+                    }
+                    continue;
+                }
+                if (kRR && rr) {
+                    for (int ch = half; ch < nchunks; ch += EPI_WARPS / 4) {
+                        // the chunk after this one: next Cout chunk, next M tile, or the first chunk of this worker's next tile
+                        const RrNext nx = ch + EPI_WARPS / 4 < nchunks ? rr_next_of(tile, mt, ch + EPI_WARPS / 4)
+                                          : (mt + 1 < mtc ? rr_next_of(tile, mt + 1, half) : rr_next_of(tile + n_workers, 0, half));
+                        const uint32_t bh = o_stage + (uint32_t)(rr_par * 2 * p.ostage), nbh = o_stage + (uint32_t)((rr_par ^ 1) * 2 * p.ostage);
+                        // (without a residual there is one buffer: rr_par stays 0)
+                        epilogue_chunk_rr<FLAGS>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, bh, bh + (uint32_t)p.ostage,
+                                                 rr_rs, nx, nbh, nbh + (uint32_t)p.ostage, lane);
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        const int yq = y0 + 16 * mt + quad * 4;
+                        if (lane == 0 && yq < p.in_H) {        // this warp's 4 rows x 8 columns x 32 channels per plane
+                            ptx::tma_store_4d(&map_o_hi, bh, n0 + ch * CW, x0, yq, n);
+                            if (p.o.out_lo) ptx::tma_store_4d(&map_o_lo, bh + (uint32_t)p.ostage, n0 + ch * CW, x0, yq, n);
+                            ptx::bulk_commit();
+                        }
+                        if (rr_rs) rr_par ^= 1;
                     }
                     continue;
                 }
@@ -1444,10 +1555,10 @@ int encode_out_map(CUtensorMap* m, const void* base, int N, int H, int W, int C,
     const cuuint64_t eb = f32 ? 4 : 2;
     const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const CUtensorMapSwizzle sw = f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    if (mode == 1) {
+    if (mode == 1 || mode == 3) {       // mode 3 (row-reuse layers): box = 32 channels x 8 columns x 4 rows, one epilogue warp's chunk
         const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         const cuuint64_t strides[3] = {(cuuint64_t)C * eb, (cuuint64_t)W * C * eb, (cuuint64_t)H * W * C * eb};
-        const cuuint32_t box[4] = {32, 30, 1, 1};
+        const cuuint32_t box[4] = {32, (cuuint32_t)(mode == 3 ? 8 : 30), (cuuint32_t)(mode == 3 ? 4 : 1), 1};
         const cuuint32_t es[4] = {1, 1, 1, 1};
         r = encode_fn()(m, dt, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1590,7 +1701,26 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         const int need = 2 * planes * (d.dxm == 2 ? 5 : 6) * 4096 + 2 * planes * bn * 128 / (pr ? 2 : 1);
         if (need > SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES - xchg_bytes - (EPI_WARPS * 2 * d.ostage + 1024)) d.ostage = 0;
     }
-    const int ostage_bytes = d.ostage ? EPI_WARPS * 2 * d.ostage + 1024 : 0;
+    d.ostage_bufs = 1;
+    // row-reuse layers with few MMAs per output value (the KernelFilter up-convolutions, conv2_1): staged in-place epilogue
+    // (epilogue_chunk_rr); RRV_NO_RSTAGE=1 is the A/B switch
+    static const bool no_rstage = getenv("RRV_NO_RSTAGE") != nullptr;
+    bool rr_stage = false;
+    if (!no_rstage && !no_ostage && !d.dxm && p->out_mode == RRV_OUT_PLANES && !p->pool && !ups && p->stats == nullptr &&
+        p->Cout % 64 == 0 && (p->ksize * p->ksize) * (p->Cin_used > 0 ? p->Cin_used : p->Cin) <= 576) {
+        const int fl = epi_flags(p->ep);
+        const bool res_ok = p->ep.res_hi == nullptr ||
+                            (!p->ep.res_f32 && p->ep.res_shift == 0 && p->ep.res_H == p->H && p->ep.res_W == p->W &&
+                             (p->ep.res_lo != nullptr) == (p->out_lo != nullptr));
+        static const bool nores = getenv("RRV_RSTAGE_NORES") != nullptr;
+        if ((fl == 0 || fl == EPI_RES || fl == (EPI_RES | EPI_N2 | EPI_AFF)) && res_ok && (p->ep.res_hi != nullptr || nores)) {
+            rr_stage = true;
+            d.ostage = 2048;
+            d.rstage = p->ep.res_hi != nullptr ? 1 : 0;
+            d.ostage_bufs = d.rstage ? 2 : 1;
+        }
+    }
+    const int ostage_bytes = d.ostage ? EPI_WARPS * 2 * d.ostage_bufs * d.ostage + 1024 : 0;
     const int budget = SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES - xchg_bytes - ostage_bytes;
     if (d.dxm == 2) {
         // ---- nearest-x2 convolution with Cout <= 64 (ResidualBlock slice2.conv1): per output parity the 3x3 convolution is a 2x2
@@ -1699,6 +1829,10 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
             BN -= 16;
             while (BN > 16 && d.Cout_pad % BN != 0) BN -= 16;
         }
+        if (rr_stage && BN % 64 != 0) {      // (a tuned-down Cout tile: each of a quadrant's two warps needs whole 32-channel chunks)
+            rr_stage = false;
+            d.ostage = 0; d.ostage_bufs = 1; d.rstage = 0;
+        }
         d.BN = BN; d.MT = MT; d.BNe = BN; d.b_tile_rows = d.Cout_pad;
         // CTA pairs everywhere except where all weight tiles can stay resident (the 64 -> 64 layers)
         const bool resident_fits = resident_shape && btiles * d.kchunks * b_slot + 2 * a_stage <= budget;
@@ -1789,14 +1923,15 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         if (encode_out_map(&t_mo_hi, p->out_f32, d.N, d.o.H, d.o.W, p->Cout, d.dxm, true)) return 1;
         t_mo_lo = t_mo_hi;
     } else if (d.ostage) {
-        if (encode_out_map(&t_mo_hi, p->out_hi, d.N, d.o.H, d.o.W, p->Cout, d.dxm)) return 1;
+        const int omode = d.dxm ? d.dxm : 3;
+        if (encode_out_map(&t_mo_hi, p->out_hi, d.N, d.o.H, d.o.W, p->Cout, omode)) return 1;
         if (p->out_lo) {
-            if (encode_out_map(&t_mo_lo, p->out_lo, d.N, d.o.H, d.o.W, p->Cout, d.dxm)) return 1;
+            if (encode_out_map(&t_mo_lo, p->out_lo, d.N, d.o.H, d.o.W, p->Cout, omode)) return 1;
         } else {
             t_mo_lo = t_mo_hi;
         }
     }
-    const int smem = d.a_stages * a_stage + d.b_slots * b_slot + d.Cout_pad * TAB_BYTES + xchg_bytes + ostage_bytes + 1024;
+    const int smem = d.a_stages * a_stage + d.b_slots * b_slot + d.Cout_pad * TAB_BYTES + xchg_bytes + (d.ostage ? ostage_bytes : 0) + 1024;
     // the specialised instantiations write planes / NHWC only; NCHW and the finished BGR frame (the RGB head) take the generic one
     const bool plain_out = p->out_mode == RRV_OUT_PLANES || p->out_mode == RRV_OUT_F32_NHWC;
     const int flags = plain_out ? epi_flags(p->ep) : -1;
