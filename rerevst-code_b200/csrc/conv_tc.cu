@@ -770,7 +770,9 @@ struct Tc2Params {
     int dxm_groups;         // weight tiles per A box: 3 (tap rows dy) or 2 (tap rows a of one row phase)
     int b_parts;            // dxm 2: TMA loads per weight slot and CTA (blocks of Cout_pad blob rows)
     int a_stages, b_slots, b_resident, pair;
-    int a_plane_bytes;      // (16 MT + 2) * 1024 (16 MT for 1x1)
+    int a_plane_bytes;      // (16 MT + 2) * 8 * row_bytes (16 MT for 1x1)
+    int row_bytes;          // bytes per operand row: 128 (64-channel chunks, SWIZZLE_128B), or 64 for a 32-channel input (SWIZZLE_64B;
+                            // row-reuse loop only: the KernelFilter up-convolutions read their 32 channels without zero padding)
     int acc_stride, set_stride, bufs, tmem_cols;
     double* stats;          // rrv_conv.stats: double[5][Cout] accumulated by the epilogue (EPI_STATS instantiations), or NULL
     int stats_minmax;
@@ -822,7 +824,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t planes = p.x3 ? 2u : 1u;
     const uint32_t a_stage_bytes = planes * (uint32_t)p.a_plane_bytes;
-    const uint32_t b_plane_bytes = (uint32_t)(PAIR ? p.BN / 2 : p.BN) * 128u;    // a pair splits the weight rows
+    const uint32_t rowb = DXM ? 128u : (uint32_t)p.row_bytes;
+    const uint32_t desc_hi = rowb == 64u ? ptx::DESC_HI_SW64 : ptx::DESC_HI_SW128;
+    const uint32_t b_plane_bytes = (uint32_t)(PAIR ? p.BN / 2 : p.BN) * rowb;    // a pair splits the weight rows
     const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
     const int cta_id = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;            // persistent worker index
     const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -1094,22 +1098,24 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         ptx::tc_fence_after();
                         const uint32_t bs = b_base + (uint32_t)slot * b_slot_bytes;
                         const bool overwrite = kc == 0 && gr.first != 0;
-                        const uint32_t a0 = a_base + (uint32_t)(gr.arow * 1024);
+                        const uint32_t a0 = a_base + (uint32_t)gr.arow * 8u * rowb;          // 8 pixels per tile row
+                        const uint32_t a1 = a0 + 128u * rowb;                                // second M tile: 16 rows further down
                         const uint32_t d0 = d_set;
                         const uint32_t bempty_bar = ptx::smem_u32(&s_bempty[sb]);
                         const uint32_t nk = kc == p.kchunks - 1 ? (uint32_t)p.nk_last : 4u;
                         if (ptx::elect_one()) {
                             if (PAIR) {
-                                ptx::mma_kblock_pair(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, (uint32_t)p.terms, overwrite, nk);
+                                ptx::mma_kblock_pair(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, (uint32_t)p.terms, overwrite, nk,
+                                                     desc_hi);
                                 if (mtc == 2)
-                                    ptx::mma_kblock_pair(d0 + (uint32_t)p.acc_stride, a0 + 16384u, a0 + 16384u + (uint32_t)p.a_plane_bytes, bs,
-                                                         bs + b_plane_bytes, idesc, (uint32_t)p.terms, overwrite, nk);
+                                    ptx::mma_kblock_pair(d0 + (uint32_t)p.acc_stride, a1, a1 + (uint32_t)p.a_plane_bytes, bs,
+                                                         bs + b_plane_bytes, idesc, (uint32_t)p.terms, overwrite, nk, desc_hi);
                                 if (!p.b_resident) ptx::mma_commit_pair(bempty_bar);
                             } else {
-                                ptx::mma_kblock(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, (uint32_t)p.terms, overwrite, nk);
+                                ptx::mma_kblock(d0, a0, a0 + (uint32_t)p.a_plane_bytes, bs, bs + b_plane_bytes, idesc, (uint32_t)p.terms, overwrite, nk, desc_hi);
                                 if (mtc == 2)
-                                    ptx::mma_kblock(d0 + (uint32_t)p.acc_stride, a0 + 16384u, a0 + 16384u + (uint32_t)p.a_plane_bytes, bs,
-                                                    bs + b_plane_bytes, idesc, (uint32_t)p.terms, overwrite, nk);
+                                    ptx::mma_kblock(d0 + (uint32_t)p.acc_stride, a1, a1 + (uint32_t)p.a_plane_bytes, bs,
+                                                    bs + b_plane_bytes, idesc, (uint32_t)p.terms, overwrite, nk, desc_hi);
                                 if (!p.b_resident) ptx::mma_commit(bempty_bar);
                             }
                         }
@@ -1157,7 +1163,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         int as = 0;
         uint32_t aphase = 0;
         // staged row-reuse epilogue (epilogue_chunk_rr): where a chunk's residual comes from, per lane
-        constexpr bool kRR = !DXM && (FLAGS == 0 || FLAGS == EPI_RES || FLAGS == (EPI_RES | EPI_N2 | EPI_AFF));
+        constexpr bool kRR = !DXM && (FLAGS == EPI_RES || FLAGS == (EPI_RES | EPI_N2 | EPI_AFF));
         const bool rr = kRR && p.ostage != 0;
         const bool rr_rs = rr && p.rstage != 0;
         int rr_par = 0;
@@ -1405,7 +1411,6 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         const RrNext nx = ch + EPI_WARPS / 4 < nchunks ? rr_next_of(tile, mt, ch + EPI_WARPS / 4)
                                           : (mt + 1 < mtc ? rr_next_of(tile, mt + 1, half) : rr_next_of(tile + n_workers, 0, half));
                         const uint32_t bh = o_stage + (uint32_t)(rr_par * 2 * p.ostage), nbh = o_stage + (uint32_t)((rr_par ^ 1) * 2 * p.ostage);
-                        // (without a residual there is one buffer: rr_par stays 0)
                         epilogue_chunk_rr<FLAGS>(p.o, e, s_tab, p.Cout_pad, ta + (uint32_t)(ch * CW), px, n0 + ch * CW, bh, bh + (uint32_t)p.ostage,
                                                  rr_rs, nx, nbh, nbh + (uint32_t)p.ostage, lane);
                         ptx::fence_proxy_async();
@@ -1416,7 +1421,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                             if (p.o.out_lo) ptx::tma_store_4d(&map_o_lo, bh + (uint32_t)p.ostage, n0 + ch * CW, x0, yq, n);
                             ptx::bulk_commit();
                         }
-                        if (rr_rs) rr_par ^= 1;
+                        rr_par ^= 1;
                     }
                     continue;
                 }
@@ -1514,14 +1519,14 @@ EncodeTiledFn encode_fn() {
 }
 
 // NHWC bf16 activation [N][H][W][C]: box = 64 channels x TW x TH x 1, 128-byte swizzle.
-int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int TW, int TH) {
+int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int TW, int TH, int row_bytes = 128) {
     const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)TW, (cuuint32_t)TH, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)(row_bytes / 2), (cuuint32_t)TW, (cuuint32_t)TH, 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     const CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(activation %dx%dx%dx%d) failed: %d", N, H, W, C, (int)r);
         return 1;
@@ -1530,14 +1535,14 @@ int encode_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C,
 }
 
 // Weights [rows = taps * Cout_pad][Cin] bf16: box = 64 channels x BN rows.
-int encode_w_map(CUtensorMap* m, const void* base, int rows, int Cin, int BN) {
+int encode_w_map(CUtensorMap* m, const void* base, int rows, int Cin, int BN, int row_bytes = 128) {
     const cuuint64_t dims[2] = {(cuuint64_t)Cin, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)Cin * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BN};
+    const cuuint32_t box[2] = {(cuuint32_t)(row_bytes / 2), (cuuint32_t)BN};
     const cuuint32_t es[2] = {1, 1};
     const CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled(weights %dx%d) failed: %d", rows, Cin, (int)r);
         return 1;
@@ -1661,8 +1666,10 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     d.in_H = p->H >> ups; d.in_W = p->W >> ups;
     d.Cout = p->Cout;
     d.Cout_pad = cout_pad_of(p->Cout);
-    d.kchunks = p->Cin / BK;
-    d.nk_last = 4;
+    const int rowb = p->Cin == 32 ? 64 : 128;        // a 32-channel input: half-width operand rows (row-reuse loop only)
+    d.row_bytes = rowb;
+    d.kchunks = (p->Cin + BK - 1) / BK;
+    d.nk_last = p->Cin == 32 ? 2 : 4;
     if (p->Cin_used > 0 && p->Cin_used < p->Cin) {      // trailing input channels that only meet zero weights: whole chunks, then k-slices
         d.kchunks = (p->Cin_used + BK - 1) / BK;
         d.nk_last = (p->Cin_used - (d.kchunks - 1) * BK + 15) / 16;
@@ -1676,7 +1683,7 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     const int btiles_tile = ups ? 4 : btiles;               // ... of which one tile (= one phase) uses this many
 
     int a_stage = 0, b_slot = 0, box_w = 8, box_rows = 0;
-    d.dxm = (g_tune.dxm && p->ksize == 3 && !ups && 3 * d.Cout_pad <= 256 && d.in_W >= 16) ? 1 : 0;
+    d.dxm = (g_tune.dxm && p->ksize == 3 && !ups && 3 * d.Cout_pad <= 256 && d.in_W >= 16 && rowb == 128) ? 1 : 0;
     static const bool no_ups_merge = getenv("RRV_NO_UPS_MERGE") != nullptr;      // A/B switch for measurements
     if (!no_ups_merge && g_tune.dxm && p->ksize == 3 && ups && 4 * d.Cout_pad <= 256 && d.Cout_pad % CW == 0 && d.in_W >= 16 &&
         (p->out_mode == RRV_OUT_PLANES || (p->out_mode == RRV_OUT_F32_NHWC && p->stats != nullptr && p->Cout == d.Cout_pad)))
@@ -1709,15 +1716,15 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     if (!no_rstage && !no_ostage && !d.dxm && p->out_mode == RRV_OUT_PLANES && !p->pool && !ups && p->stats == nullptr &&
         p->Cout % 64 == 0 && (p->ksize * p->ksize) * (p->Cin_used > 0 ? p->Cin_used : p->Cin) <= 576) {
         const int fl = epi_flags(p->ep);
-        const bool res_ok = p->ep.res_hi == nullptr ||
-                            (!p->ep.res_f32 && p->ep.res_shift == 0 && p->ep.res_H == p->H && p->ep.res_W == p->W &&
-                             (p->ep.res_lo != nullptr) == (p->out_lo != nullptr));
-        static const bool nores = getenv("RRV_RSTAGE_NORES") != nullptr;
-        if ((fl == 0 || fl == EPI_RES || fl == (EPI_RES | EPI_N2 | EPI_AFF)) && res_ok && (p->ep.res_hi != nullptr || nores)) {
+        const bool res_ok = !p->ep.res_f32 && p->ep.res_shift == 0 && p->ep.res_H == p->H && p->ep.res_W == p->W &&
+                            (p->ep.res_lo != nullptr) == (p->out_lo != nullptr);
+        // (staging the stores alone -- layers without a residual, e.g. conv2_1 -- measured slower than the direct stores: the
+        //  staging rows cost ring slots and the stores were not what those epilogues wait for)
+        if ((fl == EPI_RES || fl == (EPI_RES | EPI_N2 | EPI_AFF)) && res_ok && p->ep.res_hi != nullptr) {
             rr_stage = true;
             d.ostage = 2048;
-            d.rstage = p->ep.res_hi != nullptr ? 1 : 0;
-            d.ostage_bufs = d.rstage ? 2 : 1;
+            d.rstage = 1;
+            d.ostage_bufs = 2;
         }
     }
     const int ostage_bytes = d.ostage ? EPI_WARPS * 2 * d.ostage_bufs * d.ostage + 1024 : 0;
@@ -1813,14 +1820,14 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         // all weight tiles resident beats sharing them between two M tiles: prefer MT = 1 if that is what fits
         const bool resident_shape = !ups && BN == d.Cout_pad && btiles * d.kchunks <= MAX_B_SLOTS;
         if (MT == 2 && resident_shape) {
-            const int b_all = btiles * d.kchunks * planes * BN * 128;
-            const int a2 = planes * (32 + 2 * halo) * 1024, a1 = planes * (16 + 2 * halo) * 1024;
+            const int b_all = btiles * d.kchunks * planes * BN * rowb;
+            const int a2 = planes * (32 + 2 * halo) * 8 * rowb, a1 = planes * (16 + 2 * halo) * 8 * rowb;
             if (b_all + 2 * a2 > budget && b_all + 2 * a1 <= budget) MT = 1;
         }
         for (;;) {
             const int acc_stride = (BN + 31) / 32 * 32;
-            a_stage = planes * (16 * MT + 2 * halo) * 1024;
-            b_slot = planes * BN * 128;
+            a_stage = planes * (16 * MT + 2 * halo) * 8 * rowb;
+            b_slot = planes * BN * rowb;
             const bool tmem_ok = MT * acc_stride <= 512;
             const bool smem_ok = 2 * a_stage + 2 * b_slot <= budget;
             if (tmem_ok && smem_ok) break;
@@ -1844,7 +1851,7 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         d.bufs = 2 * d.set_stride <= 512 ? 2 : 1;
         d.tmem_cols = 32;
         while (d.tmem_cols < d.bufs * d.set_stride) d.tmem_cols *= 2;
-        d.a_plane_bytes = (16 * MT + 2 * halo) * 1024;
+        d.a_plane_bytes = (16 * MT + 2 * halo) * 8 * rowb;
 
         // ---- rings ----
         const int b_all = btiles * d.kchunks;
@@ -1860,6 +1867,7 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
                 if (d.b_slots < 4 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
                 if (d.a_stages < 3 && rem >= a_stage) { ++d.a_stages; rem -= a_stage; continue; }
                 if (d.b_slots < 8 && rem >= b_slot) { ++d.b_slots; rem -= b_slot; continue; }
+                if (rowb == 64 && d.a_stages < 6 && rem >= a_stage) { ++d.a_stages; rem -= a_stage; continue; }      // (three boxes per tile)
                 break;
             }
         }
@@ -1906,12 +1914,12 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     const int rows = btiles * d.Cout_pad;
     const uint16_t* w_hi = (const uint16_t*)p->w_tc;
     const uint16_t* w_lo = w_hi + (long long)rows * p->Cin;
-    if (encode_act_map(&ma_hi, p->in_hi, d.N, d.in_H, d.in_W, p->Cin, box_w, box_rows)) return 1;
+    if (encode_act_map(&ma_hi, p->in_hi, d.N, d.in_H, d.in_W, p->Cin, box_w, box_rows, rowb)) return 1;
     const int b_box = d.dxm == 2 ? d.Cout_pad : (d.pair ? d.BN / 2 : d.BN);
-    if (encode_w_map(&mb_hi, w_hi, rows, p->Cin, b_box)) return 1;
+    if (encode_w_map(&mb_hi, w_hi, rows, p->Cin, b_box, rowb)) return 1;
     if (d.x3) {
-        if (encode_act_map(&ma_lo, p->in_lo, d.N, d.in_H, d.in_W, p->Cin, box_w, box_rows)) return 1;
-        if (encode_w_map(&mb_lo, w_lo, rows, p->Cin, b_box)) return 1;
+        if (encode_act_map(&ma_lo, p->in_lo, d.N, d.in_H, d.in_W, p->Cin, box_w, box_rows, rowb)) return 1;
+        if (encode_w_map(&mb_lo, w_lo, rows, p->Cin, b_box, rowb)) return 1;
     } else {
         ma_lo = ma_hi;
         mb_lo = mb_hi;
@@ -2004,7 +2012,7 @@ int tc_tune_pdl(int enable) {
 }
 
 long long tc_weight_bytes(int Cin, int Cout, int ksize, int ups) {
-    if (Cin <= 0 || Cout <= 0 || Cin % BK != 0) return 0;          // the FFMA kernel takes the other shapes
+    if (Cin <= 0 || Cout <= 0 || (Cin % BK != 0 && !(Cin == 32 && !ups))) return 0;          // the FFMA kernel takes the other shapes
     if (!(ksize == 3 || (ksize == 1 && !ups))) return 0;
     const long long ntaps = ups ? 16 : ksize * ksize;
     return 2LL * ntaps * cout_pad_of(Cout) * Cin * 2;
@@ -2028,7 +2036,7 @@ int conv2d_tc(const rrv_conv* p, cudaStream_t st) {
     RRV_REQUIRE(g_lo_fp16 == 0, "rrv_conv2d(tcgen05): the tensor-core path needs bf16 lo planes (rrv_set_lo_format(0))");
     const int ups = p->ups ? 1 : 0;
     RRV_REQUIRE(tc_weight_bytes(p->Cin, p->Cout, p->ksize, ups) > 0,
-                "rrv_conv2d(tcgen05): unsupported shape Cin=%d Cout=%d k=%d ups=%d (Cin must be a multiple of 64)", p->Cin,
+                "rrv_conv2d(tcgen05): unsupported shape Cin=%d Cout=%d k=%d ups=%d (Cin must be 32 or a multiple of 64)", p->Cin,
                 p->Cout, p->ksize, ups);
     RRV_REQUIRE(p->w_tc != nullptr, "rrv_conv2d(tcgen05): w_tc is NULL");
     RRV_REQUIRE(p->in_hi != nullptr, "rrv_conv2d: in_hi is NULL");

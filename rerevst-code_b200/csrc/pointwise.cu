@@ -433,11 +433,12 @@ int pack_weights_f32(const float* w, int Cin, int Cout, int ksize, int Cin_pad, 
 // The two predicted 32x32 matrices of a KernelFilter (apply_filter, style_network_global.py:194-217) are absorbed by the
 // neighbouring convolutions:  Wf1 . conv_down(x) = conv_{Wf1 . Wdown}(x),  conv_up(Wf2 . t) = conv_{Wup . Wf2}(t).
 // This kernel computes both products in fp32 and writes them straight into the tensor-core weight blobs
-// ([tap][Cout_pad][Cin] bf16 hi, then lo; the 32 inner channels zero-padded to 64), plus the folded down bias:
+// ([tap][Cout_pad][Cin] bf16 hi, then lo; 32 inner channels), plus the folded down bias:
 // frame mode predicts new filters for every frame, so the fold must not cost library GEMMs, allocations and repack launches.
 namespace rrv {
 
-constexpr int KF_IN = 32, KF_PAD = 64, KF_C = 512;
+constexpr int KF_IN = 32, KF_PAD = 32, KF_C = 512;      // (KF_PAD: the inner channels as the blobs carry them -- no padding since the
+                                                          //  tensor-core path reads 32-channel operands as 64-byte rows)
 
 __global__ void __launch_bounds__(256) fold_filter_kernel(const float* __restrict__ wf1, const float* __restrict__ wf2,
                                                           const float* __restrict__ down_w, const float* __restrict__ down_b,
@@ -448,7 +449,7 @@ __global__ void __launch_bounds__(256) fold_filter_kernel(const float* __restric
     __syncthreads();
     const long long n_down = 9LL * KF_PAD * KF_C, n_up = 9LL * KF_C * KF_PAD;
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_down + n_up + KF_PAD; i += (long long)gridDim.x * 256) {
-        if (i < n_down) {                       // down blob: [t][co (64)][ci (512)]
+        if (i < n_down) {                       // down blob: [t][co (32)][ci (512)]
             const int ci = (int)(i % KF_C), co = (int)((i / KF_C) % KF_PAD), t = (int)(i / ((long long)KF_C * KF_PAD));
             float v = 0.0f;
             if (co < KF_IN) {
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(256) fold_filter_kernel(const float* __restric
             split_hi_lo(v, 0, h, l);
             down_blob[i] = h;
             down_blob[n_down + i] = l;
-        } else if (i < n_down + n_up) {         // up blob: [t][o (512)][ci (64)]
+        } else if (i < n_down + n_up) {         // up blob: [t][o (512)][ci (32)]
             const long long k = i - n_down;
             const int ci = (int)(k % KF_PAD), o = (int)((k / KF_PAD) % KF_C), t = (int)(k / ((long long)KF_PAD * KF_C));
             float v = 0.0f;
@@ -471,7 +472,7 @@ __global__ void __launch_bounds__(256) fold_filter_kernel(const float* __restric
             split_hi_lo(v, 0, h, l);
             up_blob[k] = h;
             up_blob[n_up + k] = l;
-        } else {                                // folded down bias, padded to 64
+        } else {                                // folded down bias
             const int co = (int)(i - n_down - n_up);
             float v = 0.0f;
             if (co < KF_IN)

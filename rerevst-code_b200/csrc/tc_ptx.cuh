@@ -153,8 +153,11 @@ __device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint6
 // constant high word (SBO = 1024 B, version 1, SWIZZLE_128B) is attached inside the asm so the whole
 // descriptor computation stays in the uniform datapath.
 constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+// rows of 64 bytes (32 bf16) written with SWIZZLE_64B: 8-row groups 512 bytes apart, layout type 4
+constexpr uint32_t DESC_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);
 __device__ __forceinline__ uint32_t desc_lo_sw128(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
-__device__ __forceinline__ void mma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
+                                            uint32_t dhi = DESC_HI_SW128) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -164,21 +167,21 @@ __device__ __forceinline__ void mma_bf16_lo(uint32_t d_tmem, uint32_t a_lo, uint
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t"
         "}\n"
-        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128)
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(dhi)
         : "memory");
 }
 // One 64-channel k-block (4 k-slices of 16) of one 128-row M tile against one weight tile.
 // Addresses are shared-memory byte addresses of the hi / lo operand planes; called by ONE thread.
 // nk < 4: only the first nk k-slices carry non-zero weights (input channels padded up to the 64-channel chunk).
 __device__ __forceinline__ void mma_kblock(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                           uint32_t idesc, uint32_t terms, bool overwrite, uint32_t nk = 4) {
+                                           uint32_t idesc, uint32_t terms, bool overwrite, uint32_t nk = 4, uint32_t dhi = DESC_HI_SW128) {
     const uint32_t ah = desc_lo_sw128(a_hi), al = desc_lo_sw128(a_lo), bh = desc_lo_sw128(b_hi), bl = desc_lo_sw128(b_lo);
 #pragma unroll
     for (uint32_t k = 0; k < 4; ++k) {           // 16 bf16 = 32 bytes = 2 descriptor units per k-slice
         if (k >= nk) break;
-        mma_bf16_lo(d_tmem, ah + 2 * k, bh + 2 * k, idesc, (overwrite && k == 0) ? 0u : 1u);
-        if (terms & 1u) mma_bf16_lo(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1u);      // hi * Wlo
-        if (terms & 2u) mma_bf16_lo(d_tmem, al + 2 * k, bh + 2 * k, idesc, 1u);      // lo * Whi
+        mma_bf16_lo(d_tmem, ah + 2 * k, bh + 2 * k, idesc, (overwrite && k == 0) ? 0u : 1u, dhi);
+        if (terms & 1u) mma_bf16_lo(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1u, dhi);      // hi * Wlo
+        if (terms & 2u) mma_bf16_lo(d_tmem, al + 2 * k, bh + 2 * k, idesc, 1u, dhi);      // lo * Whi
     }
 }
 
@@ -234,7 +237,8 @@ __device__ __forceinline__ void tmem_relinquish_pair() {
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void mma_bf16_lo_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mma_bf16_lo_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate,
+                                                 uint32_t dhi = DESC_HI_SW128) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -244,18 +248,18 @@ __device__ __forceinline__ void mma_bf16_lo_pair(uint32_t d_tmem, uint32_t a_lo,
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t"
         "}\n"
-        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(DESC_HI_SW128)
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(dhi)
         : "memory");
 }
 __device__ __forceinline__ void mma_kblock_pair(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo,
-                                                uint32_t idesc, uint32_t terms, bool overwrite, uint32_t nk = 4) {
+                                                uint32_t idesc, uint32_t terms, bool overwrite, uint32_t nk = 4, uint32_t dhi = DESC_HI_SW128) {
     const uint32_t ah = desc_lo_sw128(a_hi), al = desc_lo_sw128(a_lo), bh = desc_lo_sw128(b_hi), bl = desc_lo_sw128(b_lo);
 #pragma unroll
     for (uint32_t k = 0; k < 4; ++k) {
         if (k >= nk) break;
-        mma_bf16_lo_pair(d_tmem, ah + 2 * k, bh + 2 * k, idesc, (overwrite && k == 0) ? 0u : 1u);
-        if (terms & 1u) mma_bf16_lo_pair(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1u);
-        if (terms & 2u) mma_bf16_lo_pair(d_tmem, al + 2 * k, bh + 2 * k, idesc, 1u);
+        mma_bf16_lo_pair(d_tmem, ah + 2 * k, bh + 2 * k, idesc, (overwrite && k == 0) ? 0u : 1u, dhi);
+        if (terms & 1u) mma_bf16_lo_pair(d_tmem, ah + 2 * k, bl + 2 * k, idesc, 1u, dhi);
+        if (terms & 2u) mma_bf16_lo_pair(d_tmem, al + 2 * k, bh + 2 * k, idesc, 1u, dhi);
     }
 }
 // Arrives on the barrier at this offset in BOTH CTAs of the pair once all prior MMAs have completed.

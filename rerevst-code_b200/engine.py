@@ -23,7 +23,8 @@ vgg_outputs_super = namedtuple("VggOutputs", ["map", "relu1_1", "relu2_1", "relu
 
 STAT_NAMES = ("norm0", "norm1", "slice4.norm1", "slice4.norm2", "norm2", "slice3.norm1", "slice3.norm2",
               "norm3", "slice2.norm1", "slice2.norm2", "norm4")
-INNER_PAD = 64          # the 32 KernelFilter channels are carried zero-padded to 64
+INNER_PAD = 32          # channels of the KernelFilter's inner tensor as stored (round 1-2a: zero-padded to 64; the tensor-core path
+                        # now reads a 32-channel operand as 64-byte rows)
 
 
 class Planes:
@@ -90,7 +91,7 @@ class FoldedFilter:
     def __init__(self, fw, device):
         lib = L.lib()
         self.down, self.up = FoldedFilter._W(), FoldedFilter._W()
-        for w, cin, cout, used in ((self.down, 512, INNER_PAD, 0), (self.up, INNER_PAD, 512, 32)):
+        for w, cin, cout, used in ((self.down, 512, INNER_PAD, 0), (self.up, INNER_PAD, 512, 32 if INNER_PAD > 32 else 0)):
             w.Cin, w.Cout, w.ksize, w.ups, w.Cin_used, w.w_f32 = cin, cout, 3, False, used, None
             w.w_tc = torch.empty(lib.rrv_tc_weight_bytes(cin, cout, 3, 0), dtype=torch.uint8, device=device)
         self.down.bias = torch.zeros(INNER_PAD, dtype=torch.float32, device=device)

@@ -18,6 +18,7 @@ LAYERS = {  # name: (H, W, Cin, Cout, k, ups)
     "u128_64": (1216, 2048, 128, 64, 3, 1), "s128_64": (608, 1024, 128, 64, 1, 0), "head": (1216, 2048, 64, 3, 3, 0),
     "s512_256": (152, 256, 512, 256, 1, 0), "s256_128": (304, 512, 256, 128, 1, 0),
     "kfup": (152, 256, 64, 512, 3, 0), "kfup3": (152, 256, 64, 512, 3, 0),
+    "kfup_32": (152, 256, 32, 512, 3, 0), "kfup_32_3": (152, 256, 32, 512, 3, 0), "kfdown_32": (152, 256, 512, 32, 3, 0),
 }
 
 
@@ -41,7 +42,7 @@ def bench(name, tunings, iters=5):
     d.in_hi, d.in_lo = L.ptr(xp.hi), L.ptr(xp.lo)
     d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
     if KF:
-        d.Cin_used = 32
+        d.Cin_used = 32 if Cin == 64 else 0
         res = Planes(1, H, W, Cout, True, dev)
         res.hi.normal_()
         res.lo.zero_()
