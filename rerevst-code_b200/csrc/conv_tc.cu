@@ -1198,7 +1198,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 constexpr bool kResS = FLAGS >= 0 && (FLAGS & EPI_RES) != 0;
                 const bool res_any = FLAGS >= 0 ? kResS : e.res_hi != nullptr;
                 const bool want = DXM ? (RRV_EPI_L2PF & 2) != 0 : (RRV_EPI_L2PF & 1) != 0;
-                if (want && res_any && !rr_rs && tile + n_workers < p.total_tiles) {
+                if (want && res_any && (!rr_rs || (RRV_EPI_L2PF & 4) != 0) && tile + n_workers < p.total_tiles) {
                     int ph2, n02, x02, y02, n2, mtc2;
                     tile_coords(p, tile + n_workers, PAIR ? 2 : 1, (int)cta_rank, cols_per_tile, rows_per_set, ph2, n02, x02, y02, n2, mtc2);
                     const int esz = e.res_f32 ? 4 : 2;
@@ -1813,7 +1813,9 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         const int k_real = (ups ? 4 : p->ksize * p->ksize) * (p->Cin_used > 0 ? p->Cin_used : p->Cin);
         if (k_real < 576 && g_tune.mt == 2 && g_tune.max_bn == 256) {
             MT = 1;
-            BN = std::min(BN, 128);
+            // (a 32-channel input issues 2 k-slices per tap: the MMAs, 64 + N / 4 cycles each whatever K is, set the pace, and wide
+            //  ones cost less per output: the KernelFilter up-convolution 0.060 -> 0.048 ms at N = 256)
+            if (rowb == 128) BN = std::min(BN, 128);
         }
         while (BN > 16 && d.Cout_pad % BN != 0) BN -= 16;
         if (d.in_H <= 16) MT = 1;
