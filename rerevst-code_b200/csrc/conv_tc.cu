@@ -776,6 +776,8 @@ struct Tc2Params {
     int acc_stride, set_stride, bufs, tmem_cols;
     double* stats;          // rrv_conv.stats: double[5][Cout] accumulated by the epilogue (EPI_STATS instantiations), or NULL
     int stats_minmax;
+    int merge_wlo;          // the RGB head: hi * Whi and hi * Wlo as ONE MMA of N = 2 BN over the adjacent hi | lo weight planes (its
+                            // MMAs cost their A fetch whatever N is); lo * Whi goes to a third column block; the epilogue adds the three
     int ostage;             // planes output through per-warp staging rows + TMA stores: bytes per plane and buffer (2048), 0 = direct stores
     int ostage_off;         // offset of the staging area (EPI_WARPS x ostage_bufs x 2 planes x ostage bytes) in dynamic shared memory
     int ostage_bufs;        // 1 (merged-tap layers), 2 (row-reuse layers: epilogue_chunk_rr alternates them)
@@ -995,7 +997,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                         const uint32_t a0 = a_base + (uint32_t)dy * 4096u;          // tap row dy: 32 pixels x 128 bytes further down the box
                         const bool overwrite = kc == 0 && dy == 0;
                         const uint32_t nk = kc == kch - 1 ? (uint32_t)p.nk_last : 4u;
-                        if (PAIR) ptx::mma_kblock_pair(d0, a0, a0 + a_plane, bs, bs + b_plane_bytes, idesc, x3, overwrite, nk);
+                        if (FLAGS == EPI_HEAD && p.merge_wlo) {
+                            // A_hi x [Whi | Wlo] (the two weight planes of the slot are adjacent: one operand of 2 BN rows), then A_lo x Whi
+                            const uint32_t idesc2 = ptx::make_idesc_bf16(PAIR ? 2 * BM : BM, 2 * p.BN);
+                            const uint32_t ah = ptx::desc_lo_sw128(a0), al = ptx::desc_lo_sw128(a0 + a_plane), bh = ptx::desc_lo_sw128(bs);
+#pragma unroll
+                            for (uint32_t k = 0; k < 4; ++k) {
+                                if (k >= nk) break;
+                                const uint32_t acc = (overwrite && k == 0) ? 0u : 1u;
+                                if (PAIR) {
+                                    ptx::mma_bf16_lo_pair(d0, ah + 2 * k, bh + 2 * k, idesc2, acc);
+                                    ptx::mma_bf16_lo_pair(d0 + 2u * (uint32_t)p.BN, al + 2 * k, bh + 2 * k, idesc, acc);
+                                } else {
+                                    ptx::mma_bf16_lo(d0, ah + 2 * k, bh + 2 * k, idesc2, acc);
+                                    ptx::mma_bf16_lo(d0 + 2u * (uint32_t)p.BN, al + 2 * k, bh + 2 * k, idesc, acc);
+                                }
+                            }
+                        } else if (PAIR) ptx::mma_kblock_pair(d0, a0, a0 + a_plane, bs, bs + b_plane_bytes, idesc, x3, overwrite, nk);
                         else ptx::mma_kblock(d0, a0, a0 + a_plane, bs, bs + b_plane_bytes, idesc, x3, overwrite, nk);
                         if (!resident) {
                             if (PAIR) ptx::mma_commit_pair(ptx::smem_u32(&s_bempty[sb]));
@@ -1288,12 +1306,34 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                 if (half == 0) {
                     const uint32_t ta = tmem_base + (uint32_t)(as * p.set_stride) + ((uint32_t)(quad * 32) << 16);
                     uint32_t a0[4], a1[4], a2[4];
+                    if (p.merge_wlo) {
+                        // column blocks [hi * Whi | hi * Wlo] (a pair interleaves them per CTA: each holds half of the rows of both
+                        // planes) and lo * Whi from column 2 BN on; row r of the weight tile = tap (r / Cout_pad), channel (r % Cout_pad)
+                        const int hb = PAIR ? p.BN / 2 : p.BN;
+                        uint32_t* acc3[3] = {a0, a1, a2};
+#pragma unroll
+                        for (int t = 0; t < 3; ++t) {
+                            const int r0 = t * p.Cout_pad;
+                            const int chi = PAIR ? (r0 < hb ? r0 : 2 * hb + (r0 - hb)) : r0;
+                            uint32_t u[4], v[4];
+                            ptx::tmem_ld4_issue(ta + (uint32_t)chi, acc3[t]);
+                            ptx::tmem_ld4_issue(ta + (uint32_t)(chi + hb), u);
+                            ptx::tmem_ld4_issue(ta + (uint32_t)(2 * p.BN + r0), v);
+                            ptx::tmem_ld4_wait(acc3[t]);
+                            ptx::tmem_ld4_wait(u);
+                            ptx::tmem_ld4_wait(v);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+                                acc3[t][c] = __float_as_uint((__uint_as_float(acc3[t][c]) + __uint_as_float(u[c])) + __uint_as_float(v[c]));
+                        }
+                    } else {
                     ptx::tmem_ld4_issue(ta, a0);
                     ptx::tmem_ld4_issue(ta + (uint32_t)p.Cout_pad, a1);
                     ptx::tmem_ld4_issue(ta + (uint32_t)(2 * p.Cout_pad), a2);
                     ptx::tmem_ld4_wait(a0);
                     ptx::tmem_ld4_wait(a1);
                     ptx::tmem_ld4_wait(a2);
+                    }
                     float x[8];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) x[c] = 0.0f;
@@ -1782,6 +1822,14 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         b_slot = planes * d.BN * 128 / (d.pair ? 2 : 1);
         d.acc_stride = (d.BN + 31) / 32 * 32;
         d.set_stride = d.acc_stride;
+        // the RGB head (same conditions as the EPI_HEAD dispatch below): three column blocks per accumulator set
+        static const bool no_merge_wlo = getenv("RRV_NO_MERGE_WLO") != nullptr;
+        const bool head_like = p->out_mode != RRV_OUT_PLANES && p->out_mode != RRV_OUT_F32_NHWC && p->Cout <= 4 && epi_flags(p->ep) == 0 &&
+                               p->ep.act == 0 && !p->pool && p->stats == nullptr;
+        if (!no_merge_wlo && head_like && d.x3 && d.terms == 3 && d.BN % 16 == 0 && 2 * d.BN <= 256 && (!d.pair || (d.BN / 2) % 8 == 0)) {
+            d.merge_wlo = 1;
+            d.set_stride = (3 * d.BN + 31) / 32 * 32;
+        }
         d.bufs = 2 * d.set_stride <= 512 ? 2 : 1;
         d.tmem_cols = 32;
         while (d.tmem_cols < d.bufs * d.set_stride) d.tmem_cols *= 2;
