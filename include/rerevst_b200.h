@@ -91,8 +91,9 @@ typedef struct rrv_conv {
     void* out_lo;           /* NULL: bf16 mode */
     float* out_f32;         /* NHWC [N][H][W][Cout], or NCHW [N][out_C][H][W] */
     int32_t out_C;          /* channels kept for RRV_OUT_F32_NCHW (3 for the RGB head) */
-    int32_t Cin_used;       /* 0, or the number of leading input channels that meet non-zero weights (KernelFilter's 32
-                             * channels are carried padded to 64: Cin = 64, Cin_used = 32); the rest is not multiplied */
+    int32_t Cin_used;       /* 0, or the number of leading input channels that meet non-zero weights (a tensor carried zero-padded
+                             * to the next 64 channels); the rest is not multiplied.  The tcgen05 path takes Cin == 32 as it is
+                             * (64-byte operand rows): KernelFilter's inner tensor needs no padding */
     int32_t pool;           /* 1: nn.MaxPool2d(2, 2) (vgg19.features[4|9|18], floor) fused behind bias + activation; the
                              * planes output is [N][H/2][W/2][Cout].  tcgen05 path, ups == 0, Cout % 32 == 0, no norm /
                              * residual / affine stage. */
@@ -129,9 +130,9 @@ int rrv_tc_tune_merge(int enable);
 int rrv_tc_tune_pdl(int enable);
 /* KernelFilter fold (apply_filter, style_network_global.py:194-217; per frame in test/style_network_frame.py:97-105): the two
  * predicted 32x32 matrices wf1, wf2 ([out][in], fp32) are multiplied into the filter's down_sample (512 -> 32) and upsample
- * (32 -> 512) 3x3 weights (PyTorch OIHW fp32) and written as tensor-core blobs: down_blob = rrv_tc_weight_bytes(512, 64, 3, 0)
- * bytes for a 512 -> 64 convolution (outputs 32..63 zero) with down_bias[64] = wf1 . down_b; up_blob =
- * rrv_tc_weight_bytes(64, 512, 3, 0) bytes for a 64 -> 512 convolution (inputs 32..63 zero: use Cin_used = 32). */
+ * (32 -> 512) 3x3 weights (PyTorch OIHW fp32) and written as tensor-core blobs: down_blob = rrv_tc_weight_bytes(512, 32, 3, 0)
+ * bytes for the 512 -> 32 convolution with down_bias[32] = wf1 . down_b; up_blob = rrv_tc_weight_bytes(32, 512, 3, 0) bytes for
+ * the 32 -> 512 convolution. */
 int rrv_fold_filter(const float* wf1, const float* wf2, const float* down_w, const float* down_b, const float* up_w,
                     void* down_blob, float* down_bias, void* up_blob, void* stream);
 /* fp32 [Cout][Cin][k][k] -> [k*k][Cin_pad][Cout_pad] fp32 (zero padded) for the FFMA path. */
