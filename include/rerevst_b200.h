@@ -128,6 +128,11 @@ int rrv_tc_tune_merge(int enable);
  * independent frames in flight on several streams turns it off while it captures their graphs: the waiting CTAs would hold exactly
  * the SMs the other frame's kernels could use (1080p, 2 frames in flight: 173 frames/s with, 180 without). */
 int rrv_tc_tune_pdl(int enable);
+/* Measurement only (tools/timeline_frame.py): while a device buffer of nslots x 4 uint64 is set, every tensor-core convolution that
+ * is launched -- or captured into a CUDA graph -- takes the next slot and records, in globaltimer nanoseconds, {first CTA start,
+ * first CTA past its griddepcontrol.wait, first CTA end, last CTA end} with atomicMin / atomicMax (initialise a slot to
+ * {~0, ~0, ~0, 0}).  nslots = 0 turns it off.  Process-global like the tuning knobs. */
+int rrv_tc_timeline(void* buf, int nslots);
 /* KernelFilter fold (apply_filter, style_network_global.py:194-217; per frame in test/style_network_frame.py:97-105): the two
  * predicted 32x32 matrices wf1, wf2 ([out][in], fp32) are multiplied into the filter's down_sample (512 -> 32) and upsample
  * (32 -> 512) 3x3 weights (PyTorch OIHW fp32) and written as tensor-core blobs: down_blob = rrv_tc_weight_bytes(512, 32, 3, 0)

@@ -50,6 +50,7 @@ SIGNATURES = {
     "rrv_tc_tune_pair": (C.c_int, [C.c_int, C.c_int]),
     "rrv_tc_tune_merge": (C.c_int, [C.c_int]),
     "rrv_tc_tune_pdl": (C.c_int, [C.c_int]),
+    "rrv_tc_timeline": (C.c_int, [_vp, C.c_int]),
     "rrv_pack_weights_f32": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     "rrv_relu_backward": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "rrv_maxpool2x2_backward": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]),

@@ -36,6 +36,7 @@ int tc_tune(int max_bn, int mt);
 int tc_tune_pair(int enable, int min_bn);
 int tc_tune_merge(int enable);
 int tc_tune_pdl(int enable);
+int tc_timeline(unsigned long long* buf, int nslots);
 int first_layer(const void* src, int src_kind, int gray, int N, int H, int W, const float* w, const float* bias,
                 void* out_hi, void* out_lo, float* out_f32, cudaStream_t st);
 int reflect_pad_u8(const void* src, int N, int H, int W, int top, int left, int PH, int PW, void* dst, cudaStream_t st);
@@ -96,6 +97,7 @@ int rrv_tc_tune(int max_bn, int mt) { return tc_tune(max_bn, mt); }
 int rrv_tc_tune_pair(int enable, int min_bn) { return tc_tune_pair(enable, min_bn); }
 int rrv_tc_tune_merge(int enable) { return tc_tune_merge(enable); }
 int rrv_tc_tune_pdl(int enable) { return tc_tune_pdl(enable); }
+int rrv_tc_timeline(void* buf, int nslots) { return tc_timeline((unsigned long long*)buf, nslots); }
 int rrv_pack_weights_f32(const float* w, int Cin, int Cout, int ksize, int Cin_pad, int Cout_pad, float* out, void* stream) {
     return pack_weights_f32(w, Cin, Cout, ksize, Cin_pad, Cout_pad, out, ST(stream));
 }

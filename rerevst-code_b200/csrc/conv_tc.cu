@@ -90,6 +90,9 @@ struct TcTune {
     int pdl = 1;            // programmatic dependent launch: the next layer's CTAs start (and wait) while this layer's last round runs
 };
 TcTune g_tune;
+// rrv_tc_timeline (measurement only): every tensor-core convolution launched while a buffer is set takes the next 4-word slot
+unsigned long long* g_tl_base = nullptr;
+int g_tl_slots = 0, g_tl_next = 0;
 
 struct OutDesc {
     int H, W, Cout, out_mode, out_C;     // H, W: the OUTPUT tensor (half the convolution's size when pool is set)
@@ -778,6 +781,7 @@ struct Tc2Params {
     int stats_minmax;
     int merge_wlo;          // the RGB head: hi * Whi and hi * Wlo as ONE MMA of N = 2 BN over the adjacent hi | lo weight planes (its
                             // MMAs cost their A fetch whatever N is); lo * Whi goes to a third column block; the epilogue adds the three
+    unsigned long long* tl; // rrv_tc_timeline: {first CTA start, first CTA past griddepcontrol.wait, first CTA end, last CTA end} in ns, or NULL
     int ostage;             // planes output through per-warp staging rows + TMA stores: bytes per plane and buffer (2048), 0 = direct stores
     int ostage_off;         // offset of the staging area (EPI_WARPS x ostage_bufs x 2 planes x ostage bytes) in dynamic shared memory
     int ostage_bufs;        // 1 (merged-tap layers), 2 (row-reuse layers: epilogue_chunk_rr alternates them)
@@ -822,6 +826,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     // prologue (barrier init, TMEM allocation, constants table, descriptor prefetch) overlaps this kernel's tail; it reads
     // and writes activations only after its own griddepcontrol.wait below, i.e. after this whole grid has completed.
     ptx::pdl_launch_dependents();
+    if (p.tl != nullptr && threadIdx.x == 0) atomicMin(p.tl + 0, ptx::globaltimer());
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t planes = p.x3 ? 2u : 1u;
@@ -880,6 +885,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     else __syncthreads();
     ptx::tc_fence_after();
     ptx::pdl_wait();                        // everything above ran while the previous kernel was still finishing
+    if (p.tl != nullptr && threadIdx.x == 0) atomicMin(p.tl + 1, ptx::globaltimer());
     const uint32_t tmem_base = s_tmem_base;
     const int rows_per_set = DXM ? 4 : 16 * p.MT;
     const int cols_per_tile = DXM ? 30 : 8;                  // merged taps: 32 input columns give 30 output columns
@@ -1503,6 +1509,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         if (PAIR) ptx::tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
         else ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
+    if (p.tl != nullptr && threadIdx.x == 0) {
+        const unsigned long long t = ptx::globaltimer();
+        atomicMin(p.tl + 2, t);
+        atomicMax(p.tl + 3, t);
+    }
 }
 
 // ---- weight repack: OIHW fp32 -> [tap][Cout_pad][Cin] bf16 hi / lo (3x3: tap = dy*3 + dx) -------------
@@ -1959,6 +1970,8 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     d.ep.lo_fp16 = 0;
     d.stats = p->stats;
     d.stats_minmax = p->stats_minmax;
+    d.tl = nullptr;
+    if (g_tl_base != nullptr && g_tl_next < g_tl_slots) d.tl = g_tl_base + 4 * (g_tl_next++);
 
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     const int rows = btiles * d.Cout_pad;
@@ -2053,6 +2066,13 @@ int tc_tune_pair(int enable, int min_bn) {
 
 int tc_tune_merge(int enable) {
     g_tune.dxm = enable ? 1 : 0;
+    return 0;
+}
+
+int tc_timeline(unsigned long long* buf, int nslots) {
+    g_tl_base = nslots > 0 ? buf : nullptr;
+    g_tl_slots = nslots > 0 ? nslots : 0;
+    g_tl_next = 0;
     return 0;
 }
 
