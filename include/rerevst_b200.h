@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RRV_ABI_VERSION 2
+#define RRV_ABI_VERSION 3
 
 /* ---- library ------------------------------------------------------------------------ */
 int         rrv_abi_version(void);

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("RRV_LIB_PATH") or os.path.join(_HERE, "csrc", "librer
 
 OUT_PLANES, OUT_F32_NHWC, OUT_F32_NCHW, OUT_BGR_F32, OUT_BGR_U8 = 0, 1, 2, 3, 4
 TERMS_FULL, TERMS_NO_WLO, TERMS_NO_ALO = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 IMPL_FFMA, IMPL_TCGEN05 = 0, 1
 
 _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64

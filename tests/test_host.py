@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     handle = ctypes.CDLL(_lib.LIB_PATH)
     for name in _header_functions():
         assert hasattr(handle, name), name
-    assert _lib.lib().rrv_abi_version() == _lib.ABI_VERSION == 2
+    assert _lib.lib().rrv_abi_version() == _lib.ABI_VERSION == 3
     assert _lib.lib().rrv_launch_count() == 0
 
 
