@@ -15,3 +15,8 @@ done
 for p in "${pids[@]}"; do wait $p; done
 $NVCC -shared -o librerevst_b200.so build/*.o -lcudart
 echo "built $(pwd)/librerevst_b200.so"
+# the optional video-output side library (include/rerevst_b200_io.h): host code + nvJPEG; nothing on the stylization path loads it
+if [ ! -f librerevst_b200_io.so ] || [ mjpg_io.cpp -nt librerevst_b200_io.so ] || [ ../../include/rerevst_b200_io.h -nt librerevst_b200_io.so ]; then
+  $NVCC -O2 -std=c++17 -Xcompiler -fPIC -shared mjpg_io.cpp -o librerevst_b200_io.so -lnvjpeg -lcudart
+fi
+echo "built $(pwd)/librerevst_b200_io.so"

@@ -86,7 +86,7 @@ class Stylization:
         upsamples), e.g. 436 x 1024 -> 432 x 1024 exactly like the reference."""
         return (H // 8) * 8, (W // 8) * 8
 
-    def transfer_stream(self, frames, crop=None, depth=4, pad_to=None, copy=True, out_dtype="f32", lanes=None):
+    def transfer_stream(self, frames, crop=None, depth=4, pad_to=None, copy=True, out_dtype="f32", lanes=None, device_sink=None):
         """Generator over an iterable of uint8 BGR frames of one size: yields exactly what
         ``transfer(frame, crop)`` returns for each, in order, but pipelined -- the pinned-memory
         upload of frame i+1 (copy-in stream) and the download of frame i-1 (copy-out stream) overlap the
@@ -103,7 +103,11 @@ class Stylization:
 
         ``lanes``: frames whose kernels run concurrently (default 2 in global mode, where a frame is one graph replay without
         shared scratch; 1 in frame mode): consecutive frames alternate between two compute streams, so that the SMs one
-        frame's layer leaves idle in its last persistent round run the other frame's kernels (engine.forward_graphed)."""
+        frame's layer leaves idle in its last persistent round run the other frame's kernels (engine.forward_graphed).
+
+        ``device_sink(i, dev_frame, stream)``: called for every frame with the finished frame still on the device ([h, w, 3] tensor
+        of ``out_dtype``, valid until the frame is yielded) and the copy-out stream current, e.g. to enqueue a GPU JPEG encode
+        (video_io.MjpgWriter.encode); if it returns a callable, that is run right before the frame is yielded."""
         if out_dtype not in ("f32", "u8"):
             raise ValueError("out_dtype must be 'f32' or 'u8'")
         t_out = torch.uint8 if out_dtype == "u8" else torch.float32
@@ -119,6 +123,9 @@ class Stylization:
 
         def finish(slot):
             slot["ev_out"].synchronize()
+            fin, slot["fin"] = slot.get("fin"), None
+            if fin is not None:
+                fin()
             out = slot["host_out"].numpy()[0]
             return out.copy() if copy else out
 
@@ -174,6 +181,8 @@ class Stylization:
             with torch.cuda.stream(s_out):
                 s_out.wait_event(slot["ev_done"])
                 slot["host_out"].copy_(slot["dev_out"], non_blocking=True)
+                if device_sink is not None:
+                    slot["fin"] = device_sink(i, slot["dev_out"][0], s_out)
                 slot["ev_out"].record(s_out)
             pending.append(slot)
         while pending:

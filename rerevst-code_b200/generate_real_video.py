@@ -8,7 +8,9 @@ constants (:21-43) as defaults, so ``python -m rerevst_code_b200.generate_real_v
   global pre-pass: clean, add every 8th frame + the last one, compute     (:129-148; frames in
                    glob order and UNPADDED, quirk Q3 -- kept)
   per frame: read → reflect-pad by 64 to a multiple of 64 → transfer → crop → imwrite   (:152-171)
-  optional MJPG .avi of the written frames                                (:175-186)
+  optional MJPG .avi of the written frames                                (:175-186; ``video_writer="nvjpeg"``: the frames
+                   are JPEG-encoded on the GPU while they are still there -- video_io.MjpgWriter -- instead of being read
+                   back from disk and encoded by cv2 on the CPU)
 
 Host image I/O (cv2) stays on the host like in the reference; the frame loop uses
 ``Stylization.transfer_stream`` so the upload of frame i+1 and the download of frame i-1 overlap the
@@ -46,7 +48,8 @@ class ReshapeTool:
 
 def main(style_img="./inputs/plum_flower.jpg", content_video="./inputs/ambush_4/*.png",
          checkpoint_path="./Model/style_net-TIP-final.pth", cuda=True, use_Global=True, save_video=True, fps=24,
-         result_frames_path="./result_frames/", result_videos_path="./result_videos/", precision="x3", verbose=True):
+         result_frames_path="./result_frames/", result_videos_path="./result_videos/", precision="x3", verbose=True,
+         video_writer="cv2", video_quality=75):
     import cv2
     from .framework import Stylization
 
@@ -87,11 +90,35 @@ def main(style_img="./inputs/plum_flower.jpg", content_video="./inputs/ambush_4/
     raw_frames = (cv2.imread(frame_list[i]) for i in range(frame_num))
     # out_dtype="u8": the frame arrives as the uint8 image cv2.imwrite would make of the reference's float32 result (:170,
     # saturate_cast<uchar>(cvRound(v))) -- the same file, a quarter of the download
-    for i, styled in enumerate(framework.transfer_stream(raw_frames, pad_to=pad_to, copy=False, out_dtype="u8")):     # written out before the next one
+    if video_writer not in ("cv2", "nvjpeg"):
+        raise ValueError("video_writer must be 'cv2' (the reference's CPU encoder) or 'nvjpeg'")
+    gpu_video = save_video and frame_num and video_writer == "nvjpeg"
+    sink, jpegs = None, {}
+    if gpu_video:
+        # Motion-JPEG on the GPU: every finished frame is encoded while it is still on the device (three encoder states rotate
+        # with the frames in flight); the bitstreams are kept and muxed in FILE-NAME order below, like the reference's sorted
+        # list of written frames (:176-177) -- frames are processed in glob order
+        from .video_io import MjpgWriter
+        vw = MjpgWriter(os.path.join(result_videos_path, name + ".avi"), fps, (first.shape[1], first.shape[0]), quality=video_quality, states=4)
+
+        def sink(i, dev_frame, stream):
+            k = i % 4
+            vw.encode(dev_frame, k, stream)
+
+            def fin():
+                jpegs[os.path.basename(frame_list[i])] = vw.retrieve(k)
+            return fin
+
+    for i, styled in enumerate(framework.transfer_stream(raw_frames, pad_to=pad_to, copy=False, out_dtype="u8", depth=4,
+                                                         device_sink=sink)):     # written out before the next one
         say("Stylizing frame %d" % i)
         cv2.imwrite(os.path.join(out_dir, os.path.basename(frame_list[i])), styled)
 
-    if save_video and frame_num:
+    if gpu_video:
+        for fname in sorted(jpegs):
+            vw.write_jpeg(jpegs[fname])
+        vw.release()
+    elif save_video and frame_num:
         written = sorted(glob.glob(os.path.join(out_dir, "*.*")))
         demo = cv2.imread(written[0])
         writer = cv2.VideoWriter(os.path.join(result_videos_path, name + ".avi"), cv2.VideoWriter_fourcc(*"MJPG"), fps,
