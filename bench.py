@@ -49,6 +49,21 @@ METRIC = "stylized frames/sec at 1080p (1/2/4/8 B200) + % conv roofline"
 TOL = 1e-3
 
 
+def host_cpu():
+    """CPU model of the host the CPU arm runs on, its logical CPUs, and the math libraries torch's CPU convolutions use."""
+    model = "unknown"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.lower().startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    cfg = torch.__config__.show()
+    libs = [k for k in ("oneDNN", "MKL-DNN", "MKL", "OpenMP") if k.lower() in cfg.lower()]
+    return {"model": model, "logical_cpus": os.cpu_count() or 1, "torch_threads": torch.get_num_threads(), "torch_cpu_libs": libs}
+
+
 def padded_size(h, w):
     """ReshapeTool, generate_real_video.py:66-78."""
     nh, nw = h + 128, w + 128
@@ -223,7 +238,7 @@ def run_reference(args):
             "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args.size, args.samples),
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": sample + f"; torch {torch.__version__} CPU"},
+                             "sample": sample + f"; torch {torch.__version__} CPU", "host": host_cpu()},
             "full_frame_steps": full,
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
@@ -682,7 +697,8 @@ def main():
         if world == 1:
             line["cpu_baseline"] = {"value": 1.0 / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"one {ph}x{pw} frame through the oracle's Stylization.transfer "
-                                              f"(torch {torch.__version__} CPU, {cores} threads), statistics imported from the GPU pre-pass"}
+                                              f"(torch {torch.__version__} CPU, {cores} threads), statistics imported from the GPU pre-pass",
+                                    "host": host_cpu()}
         else:
             line["cpu_baseline"] = None
         if args.precision == "x3":
