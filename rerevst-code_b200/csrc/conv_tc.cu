@@ -23,8 +23,11 @@
 // are four GEMMs over the same low-res tile that scatter to interleaved output pixels.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread) and TMEM owner,
 // warps 2..9 = epilogue (tcgen05.ld -> fused pointwise chain -> stores; the merged-tap layers stage
-// their rows in shared memory and leave through TMA stores); the per-channel constants of the chain
-// are gathered once per CTA into a shared-memory table.
+// their rows in shared memory and leave through TMA stores; row-reuse layers with a same-size residual
+// bring it in by cp.async one chunk ahead and run the chain in place: epilogue_chunk_rr); the
+// per-channel constants of the chain are gathered once per CTA into a shared-memory table.
+// Operand rows are 128 bytes (64 channels, SWIZZLE_128B) or, for a 32-channel input in the row-reuse
+// loop, 64 bytes (SWIZZLE_64B boxes and descriptors).
 #include <cuda.h>
 #include <math_constants.h>
 
