@@ -15,7 +15,7 @@ layers += [("conv1_2 + pool", px(1) * 64 * E, px(2) * 64 * E), ("conv2_1", px(2)
            ("conv3_2", px(4) * 256 * E, px(4) * 256 * E), ("conv3_3", px(4) * 256 * E, px(4) * 256 * E),
            ("conv3_4 + pool", px(4) * 256 * E, px(8) * 256 * E), ("conv4_1 + norm0", px(8) * 256 * E, px(8) * 512 * E)]
 for i in range(3):
-    layers += [(f"Filter{i + 1}.down", px(8) * 512 * E, px(8) * 64 * E), (f"Filter{i + 1}.up + res", px(8) * (64 + 512) * E, px(8) * 512 * E)]
+    layers += [(f"Filter{i + 1}.down", px(8) * 512 * E, px(8) * 32 * E), (f"Filter{i + 1}.up + res", px(8) * (32 + 512) * E, px(8) * 512 * E)]
 for name, s, cin, cout in (("slice4", 8, 512, 256), ("slice3", 4, 256, 128), ("slice2", 2, 128, 64)):
     layers += [(f"{name}.shortcut (fp32 out)", px(s) * cin * E, px(s) * cout * 4),
                (f"{name}.conv1 (x2)", px(s) * cin * E, px(s // 2) * cout * E),
