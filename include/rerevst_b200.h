@@ -114,9 +114,10 @@ int rrv_conv2d(const rrv_conv* p, int impl, void* stream);
  * w_oihw: fp32 [Cout][Cin][k][k] (PyTorch layout) on the device. */
 int64_t rrv_tc_weight_bytes(int Cin, int Cout, int ksize, int ups);
 int rrv_pack_weights_tc(const float* w_oihw, int Cin, int Cout, int ksize, int ups, void* blob, void* stream);
-/* Tuning knobs of the tensor-core kernel, for kernel development and the variant tests (process-global, not thread-safe: set
- * them before any other thread launches convolutions).  Defaults 256, 2: widest Cout tile; 128-pixel M tiles per weight tile
- * in the row-reuse main loop (1 | 2). */
+/* Tuning knobs of the tensor-core kernel, for kernel development and the variant tests.  Process-global; the setters and the
+ * convolution calls synchronise on one mutex and every rrv_conv2d call works from ONE snapshot of the knobs, so a call never
+ * sees half an update -- but a knob flipped by one thread does change what other threads' later calls do.  Defaults 256, 2:
+ * widest Cout tile; 128-pixel M tiles per weight tile in the row-reuse main loop (1 | 2). */
 int rrv_tc_tune(int max_bn, int mt);
 /* CTA pairs (tcgen05 cta_group::2, clusters of 2): enabled by default for Cout tiles >= min_bn (64). */
 int rrv_tc_tune_pair(int enable, int min_bn);

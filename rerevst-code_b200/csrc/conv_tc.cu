@@ -92,7 +92,12 @@ struct TcTune {
     int pair_min_bn = 64;   // (<= 64 also overrides resident weights: measured faster on the 64 -> 64 layers)
     int pdl = 1;            // programmatic dependent launch: the next layer's CTAs start (and wait) while this layer's last round runs
 };
-TcTune g_tune;
+TcTune g_tune;                  // written by the rrv_tc_tune* setters, read as ONE snapshot per convolution call (both under g_tune_mu):
+std::mutex g_tune_mu;           // a call never sees half of a setter's update, whatever thread flips the knobs
+TcTune tune_snapshot() {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
+    return g_tune;
+}
 // rrv_tc_timeline (measurement only): every tensor-core convolution launched while a buffer is set takes the next 4-word slot
 unsigned long long* g_tl_base = nullptr;
 int g_tl_slots = 0, g_tl_next = 0;
@@ -784,6 +789,7 @@ struct Tc2Params {
     int stats_minmax;
     int merge_wlo;          // the RGB head: hi * Whi and hi * Wlo as ONE MMA of N = 2 BN over the adjacent hi | lo weight planes (its
                             // MMAs cost their A fetch whatever N is); lo * Whi goes to a third column block; the epilogue adds the three
+    int pdl_attr;           // launch with the programmatic-stream-serialization attribute (the tuning snapshot of this call)
     unsigned long long* tl; // rrv_tc_timeline: {first CTA start, first CTA past griddepcontrol.wait, first CTA end, last CTA end} in ns, or NULL
     int ostage;             // planes output through per-warp staging rows + TMA stores: bytes per plane and buffer (2048), 0 = direct stores
     int ostage_off;         // offset of the staging area (EPI_WARPS x ostage_bufs x 2 planes x ostage bytes) in dynamic shared memory
@@ -1692,7 +1698,7 @@ int launch_tc2p(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, c
         attr[na].val.clusterDim.z = 1;
         ++na;
     }
-    if (!no_pdl && g_tune.pdl) {
+    if (!no_pdl && d.pdl_attr) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;
@@ -1712,6 +1718,7 @@ int launch_tc2(int grid, int smem, cudaStream_t st, const CUtensorMap& ma_hi, co
 }
 
 int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
+    const TcTune tune = tune_snapshot();
     const int ups = p->ups ? 1 : 0;
     Tc2Params d;
     memset(&d, 0, sizeof(d));
@@ -1737,9 +1744,9 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     const int btiles_tile = ups ? 4 : btiles;               // ... of which one tile (= one phase) uses this many
 
     int a_stage = 0, b_slot = 0, box_w = 8, box_rows = 0;
-    d.dxm = (g_tune.dxm && p->ksize == 3 && !ups && 3 * d.Cout_pad <= 256 && d.in_W >= 16 && rowb == 128) ? 1 : 0;
+    d.dxm = (tune.dxm && p->ksize == 3 && !ups && 3 * d.Cout_pad <= 256 && d.in_W >= 16 && rowb == 128) ? 1 : 0;
     static const bool no_ups_merge = getenv("RRV_NO_UPS_MERGE") != nullptr;      // A/B switch for measurements
-    if (!no_ups_merge && g_tune.dxm && p->ksize == 3 && ups && 4 * d.Cout_pad <= 256 && d.Cout_pad % CW == 0 && d.in_W >= 16 &&
+    if (!no_ups_merge && tune.dxm && p->ksize == 3 && ups && 4 * d.Cout_pad <= 256 && d.Cout_pad % CW == 0 && d.in_W >= 16 &&
         (p->out_mode == RRV_OUT_PLANES || (p->out_mode == RRV_OUT_F32_NHWC && p->stats != nullptr && p->Cout == d.Cout_pad)))
         d.dxm = 2;
     const int xchg_bytes = (p->pool && d.dxm) ? EPI_WARPS * 512 : 0;       // row-partner exchange of the fused max-pool
@@ -1756,9 +1763,9 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
                             ((d.dxm == 1 && p->Cout % CW == 0) || (d.dxm == 2 && p->Cout == 64));
     if (ostage_f32) d.ostage = 2048;
     if (d.ostage) {      // the staging rows must leave room for two A stages and two weight slots (CTA pairs halve the weight slots)
-        const bool pair_ok = g_tune.pair && num_sms() % 2 == 0;
+        const bool pair_ok = tune.pair && num_sms() % 2 == 0;
         const int bn = (d.dxm == 2 ? 4 : 3) * d.Cout_pad;
-        const bool pr = d.dxm == 2 ? pair_ok : (pair_ok && bn >= std::min(g_tune.pair_min_bn, 48) && (bn / 2) % 8 == 0);
+        const bool pr = d.dxm == 2 ? pair_ok : (pair_ok && bn >= std::min(tune.pair_min_bn, 48) && (bn / 2) % 8 == 0);
         const int need = 2 * planes * (d.dxm == 2 ? 5 : 6) * 4096 + 2 * planes * bn * 128 / (pr ? 2 : 1);
         if (need > SMEM_LIMIT - 1024 - d.Cout_pad * TAB_BYTES - xchg_bytes - (EPI_WARPS * 2 * d.ostage + 1024)) d.ostage = 0;
     }
@@ -1793,7 +1800,7 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         d.nph = 2;
         d.BN = 4 * d.Cout_pad; d.BNe = d.Cout_pad; d.b_tile_rows = d.Cout_pad;
         d.n_ntiles = 1;
-        d.pair = (g_tune.pair && num_sms() % 2 == 0) ? 1 : 0;
+        d.pair = (tune.pair && num_sms() % 2 == 0) ? 1 : 0;
         d.a_plane_bytes = 5 * 4096;
         a_stage = planes * d.a_plane_bytes;
         b_slot = planes * d.BN * 128 / (d.pair ? 2 : 1);
@@ -1829,8 +1836,8 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         // (each CTA of a pair holds BN / 2 weight rows: whole 8-row swizzle atoms.  The RGB head, N = 48, is a pair too -- its MMAs
         //  cost their A fetch, 64 cycles, whatever N is, and a pair covers twice the pixels per MMA; RRV_HEAD_PAIR=0 is the A/B switch)
         static const bool head_pair = !(getenv("RRV_HEAD_PAIR") && atoi(getenv("RRV_HEAD_PAIR")) == 0);
-        const int min_bn = head_pair ? std::min(g_tune.pair_min_bn, 48) : g_tune.pair_min_bn;
-        d.pair = (g_tune.pair && num_sms() % 2 == 0 && d.BN >= min_bn && (d.BN / 2) % 8 == 0) ? 1 : 0;
+        const int min_bn = head_pair ? std::min(tune.pair_min_bn, 48) : tune.pair_min_bn;
+        d.pair = (tune.pair && num_sms() % 2 == 0 && d.BN >= min_bn && (d.BN / 2) % 8 == 0) ? 1 : 0;
         d.a_plane_bytes = 6 * 4096;
         a_stage = planes * d.a_plane_bytes;
         b_slot = planes * d.BN * 128 / (d.pair ? 2 : 1);
@@ -1868,12 +1875,12 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         d.tiles_y = ceil_div(d.in_H, 4);
     } else {
         // ---- tile shape: Cout tile BN, M tiles per weight tile MT ----
-        int BN = std::min(d.Cout_pad, g_tune.max_bn);
-        int MT = std::max(1, std::min(g_tune.mt, 2));
+        int BN = std::min(d.Cout_pad, tune.max_bn);
+        int MT = std::max(1, std::min(tune.mt, 2));
         // few MMAs per output value (the 1x1 shortcuts, the KernelFilter up-convolutions): the epilogue is the kernel's time and
         // nothing is gained from sharing a weight tile between two M tiles; smaller work items balance the 148 SMs better
         const int k_real = (ups ? 4 : p->ksize * p->ksize) * (p->Cin_used > 0 ? p->Cin_used : p->Cin);
-        if (k_real < 576 && g_tune.mt == 2 && g_tune.max_bn == 256) {
+        if (k_real < 576 && tune.mt == 2 && tune.max_bn == 256) {
             MT = 1;
             // (a 32-channel input issues 2 k-slices per tap: the MMAs, 64 + N / 4 cycles each whatever K is, set the pace, and wide
             //  ones cost less per output: the KernelFilter up-convolution 0.060 -> 0.048 ms at N = 256)
@@ -1907,7 +1914,7 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
         d.BN = BN; d.MT = MT; d.BNe = BN; d.b_tile_rows = d.Cout_pad;
         // CTA pairs everywhere except where all weight tiles can stay resident (the 64 -> 64 layers)
         const bool resident_fits = resident_shape && btiles * d.kchunks * b_slot + 2 * a_stage <= budget;
-        d.pair = (g_tune.pair && (!resident_fits || g_tune.pair_min_bn <= 64) && BN >= g_tune.pair_min_bn && BN % 32 == 0 && num_sms() % 2 == 0) ? 1 : 0;
+        d.pair = (tune.pair && (!resident_fits || tune.pair_min_bn <= 64) && BN >= tune.pair_min_bn && BN % 32 == 0 && num_sms() % 2 == 0) ? 1 : 0;
         if (d.pair) b_slot /= 2;
         d.n_ntiles = d.Cout_pad / BN;
         d.acc_stride = (BN + 31) / 32 * 32;
@@ -1973,6 +1980,7 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
     d.ep.lo_fp16 = 0;
     d.stats = p->stats;
     d.stats_minmax = p->stats_minmax;
+    d.pdl_attr = tune.pdl;
     d.tl = nullptr;
     if (g_tl_base != nullptr && g_tl_next < g_tl_slots) d.tl = g_tl_base + 4 * (g_tl_next++);
 
@@ -2055,6 +2063,7 @@ int conv2d_tc2(const rrv_conv* p, cudaStream_t st) {
 int tc_tune(int max_bn, int mt) {
     RRV_REQUIRE(max_bn >= 16 && max_bn <= 256 && max_bn % 16 == 0, "rrv_tc_tune: max_bn must be a multiple of 16 in [16, 256]");
     RRV_REQUIRE(mt == 1 || mt == 2, "rrv_tc_tune: mt must be 1 or 2");
+    std::lock_guard<std::mutex> lk(g_tune_mu);
     g_tune.max_bn = max_bn;
     g_tune.mt = mt;
     return 0;
@@ -2062,12 +2071,14 @@ int tc_tune(int max_bn, int mt) {
 
 int tc_tune_pair(int enable, int min_bn) {
     RRV_REQUIRE(min_bn >= 32 && min_bn <= 256 && min_bn % 32 == 0, "rrv_tc_tune_pair: min_bn must be a multiple of 32 in [32, 256]");
+    std::lock_guard<std::mutex> lk(g_tune_mu);
     g_tune.pair = enable ? 1 : 0;
     g_tune.pair_min_bn = min_bn;
     return 0;
 }
 
 int tc_tune_merge(int enable) {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
     g_tune.dxm = enable ? 1 : 0;
     return 0;
 }
@@ -2080,6 +2091,7 @@ int tc_timeline(unsigned long long* buf, int nslots) {
 }
 
 int tc_tune_pdl(int enable) {
+    std::lock_guard<std::mutex> lk(g_tune_mu);
     g_tune.pdl = enable ? 1 : 0;
     return 0;
 }
