@@ -216,8 +216,8 @@ def test_conv_full_epilogue_chain(L, dev, size):
 
 
 @pytest.mark.parametrize("size", [(1, 19, 40), (2, 36, 21), (1, 152, 64)])
-@pytest.mark.parametrize("cin,chain", [(32, False), (32, True), (64, True)])
-def test_kernelfilter_upsample_epilogue(L, dev, size, cin, chain):
+@pytest.mark.parametrize("cin,chain,pair", [(32, False, 1), (32, True, 1), (64, True, 1), (32, True, 0), (64, False, 0)])
+def test_kernelfilter_upsample_epilogue(L, dev, size, cin, chain, pair):
     """KernelFilter.forward's `x + upsample(t)` (style_network_global.py:217), for Filter3 followed by Decoder.norm[1] + AdaIN
     (:443): conv3x3 cin -> 512 + bias + residual planes at the same resolution [+ saved-stat norm + affine].  On the tensor-core
     path this is the staged row-reuse epilogue (residual by cp.async one chunk ahead, chain in place, TMA store) over 64-byte
@@ -240,17 +240,21 @@ def test_kernelfilter_upsample_epilogue(L, dev, size, cin, chain):
         sc, sh = torch.rand(Cc, generator=g) + 0.5, torch.randn(Cc, generator=g)
         ref = stylenet.in_forward(ref, st) * sc.view(1, -1, 1, 1) + sh.view(1, -1, 1, 1)
         kw = dict(norm2=torch.stack([x.reshape(-1) for x in st]).contiguous().to(dev), affine=torch.stack([sc, sh]).contiguous().to(dev))
-    for name, impl in _impls(L):
-        d = L.Conv()
-        d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = N, H, W, cin, Cc, 3, 0
-        d.in_hi, d.in_lo = L.ptr(tp.hi), L.ptr(tp.lo)
-        d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
-        d.ep = make_epilogue(bias=cw.bias, res=rp, **kw)
-        o = Planes(N, H, W, Cc, True, dev)
-        o.hi.fill_(float("nan"))
-        d.out_mode, d.out_hi, d.out_lo = L.OUT_PLANES, L.ptr(o.hi), L.ptr(o.lo)
-        L.check(L.lib().rrv_conv2d(C.byref(d), impl, L.stream()), name)
-        assert rel_linf(_from_planes(L, o).cpu(), ref) < 2e-4, (name, size, cin, chain)
+    L.check(L.lib().rrv_tc_tune_pair(pair, 64))            # pair = 0: the single-CTA instantiation of the same path
+    try:
+        for name, impl in _impls(L):
+            d = L.Conv()
+            d.N, d.H, d.W, d.Cin, d.Cout, d.ksize, d.ups = N, H, W, cin, Cc, 3, 0
+            d.in_hi, d.in_lo = L.ptr(tp.hi), L.ptr(tp.lo)
+            d.w_f32, d.w_tc = L.ptr(cw.w_f32), L.ptr(cw.w_tc)
+            d.ep = make_epilogue(bias=cw.bias, res=rp, **kw)
+            o = Planes(N, H, W, Cc, True, dev)
+            o.hi.fill_(float("nan"))
+            d.out_mode, d.out_hi, d.out_lo = L.OUT_PLANES, L.ptr(o.hi), L.ptr(o.lo)
+            L.check(L.lib().rrv_conv2d(C.byref(d), impl, L.stream()), name)
+            assert rel_linf(_from_planes(L, o).cpu(), ref) < 2e-4, (name, size, cin, chain, pair)
+    finally:
+        L.check(L.lib().rrv_tc_tune_pair(1, 64))
 
 
 @pytest.mark.parametrize("kind,gray", [(0, 1), (0, 0), (1, 1), (1, 0)])
